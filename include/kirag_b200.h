@@ -1,0 +1,193 @@
+/*
+ * kirag_b200.h — C ABI of the B200-native (sm_100a) exact inner-product top-k
+ * search and the mean-pool + L2-normalise embedding epilogue.
+ *
+ * This is the drop-in boundary for the one native dependency on KiRAG's
+ * dense-retrieval hot path: the `faiss` module object as seen by
+ * /root/reference/retriever/index.py:6.  Every entry point below names the
+ * reference call site it replaces.  All signatures are plain C: pointers,
+ * sizes, ints.  No torch / numpy types cross this boundary.
+ *
+ * Conventions
+ *   - every function returning `int` returns 0 on success, non-zero on
+ *     failure; the message is in kirag_last_error() (thread-local).  The
+ *     library never calls abort()/exit().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *     stream).  Host-pointer entry points are synchronous (results are ready
+ *     on return, like FAISS).  Device-pointer entry points are stream-ordered
+ *     except where noted.
+ *   - inputs are borrowed for the duration of the call; outputs are
+ *     caller-owned buffers.  The index owns its copy of the corpus (FAISS
+ *     copies on add(), reference call site retriever/index.py:32).
+ *   - there is NO CPU fallback.  If no CUDA device is usable every call fails
+ *     with a non-zero status.
+ */
+#ifndef KIRAG_B200_H
+#define KIRAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KIRAG_ABI_VERSION 1
+
+/* metric ids; only inner product is implemented, as only inner product is
+ * ever constructed by the reference (retrieve.py:112, faiss_index_corpus.py:29) */
+#define KIRAG_METRIC_INNER_PRODUCT 0
+#define KIRAG_METRIC_L2 1
+
+/* search path selectors for kirag_index_search_ex() */
+#define KIRAG_PATH_AUTO 0   /* tcgen05 bf16 filter scan + fp32 rescoring, certified; exact fp32 scan for uncertified queries */
+#define KIRAG_PATH_EXACT 1  /* fp32 CUDA-core scan of the fp32 master only */
+#define KIRAG_PATH_FAST 2   /* bf16 filter scan + rescoring, certificate evaluated and reported but not acted on */
+
+/* hidden-state dtypes for kirag_pool_normalize() */
+#define KIRAG_DTYPE_F32 0
+#define KIRAG_DTYPE_BF16 1
+#define KIRAG_DTYPE_F16 2
+
+/* mask dtypes */
+#define KIRAG_MASK_I64 0
+#define KIRAG_MASK_I32 1
+#define KIRAG_MASK_U8 2
+
+/* pooling modes */
+#define KIRAG_POOL_MEAN 0 /* E5Encoder.forward tail: retriever/encoders.py:56-58,75-76 */
+#define KIRAG_POOL_CLS 1  /* BGEEncoder.forward tail: retriever/encoders.py:115-117 */
+
+typedef struct kirag_index kirag_index_t;
+
+/* per-call search statistics (all counts are queries unless noted) */
+typedef struct kirag_search_stats {
+    int64_t nq;              /* queries in the call */
+    int64_t n_fast;          /* answered by the tcgen05 filter path with a passing certificate */
+    int64_t n_exact;         /* answered by the exact fp32 scan (forced, ineligible shape, or escalated) */
+    int64_t n_cert_fail;     /* certificate failures observed on the filter path */
+    int64_t n_overflow;      /* candidate-buffer overflows observed on the filter path */
+    int32_t levels;          /* filter launches (geometric levels) of the last query chunk */
+    int32_t path;            /* path actually taken for the bulk of the call (KIRAG_PATH_*) */
+    int64_t kernel_launches; /* kernels launched by this library during the call */
+} kirag_search_stats_t;
+
+/* ---- library ---------------------------------------------------------- */
+
+/* ABI version of the loaded library (== KIRAG_ABI_VERSION it was built with). */
+int kirag_abi_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* kirag_last_error(void);
+
+/* Number of usable CUDA devices (0 if none / no driver).  Never fails. */
+int kirag_device_count(void);
+
+/* ---- flat inner-product index  (replaces faiss.IndexFlatIP) ------------ */
+
+/* faiss.IndexFlatIP(d)                      retriever/index.py:13,23 */
+int kirag_index_create(int d, int metric, int device, kirag_index_t** out);
+
+/* destructor of the faiss index object */
+int kirag_index_destroy(kirag_index_t* h);
+
+/* Pre-size device storage for n_total rows (optional; add() grows as needed). */
+int kirag_index_reserve(kirag_index_t* h, int64_t n_total);
+
+/* index.add(x)                              retriever/index.py:32
+ * x: row-major float32 [n, d]; host pointer (x_is_device == 0) or device
+ * pointer on the index's device.  Rows get implicit ids ntotal .. ntotal+n-1. */
+int kirag_index_add(kirag_index_t* h, const float* x, int64_t n, int x_is_device, void* stream);
+
+/* index.ntotal                              retriever/index.py:74,79 */
+int64_t kirag_index_ntotal(const kirag_index_t* h);
+
+/* index.d */
+int kirag_index_dim(const kirag_index_t* h);
+
+/* index.search(x, k)                        retriever/index.py:47
+ * q: float32 [nq, d]; D: float32 [nq, k]; I: int64 [nq, k].
+ * Rows of D/I are ordered by (score descending, id ascending); unfilled slots
+ * (k > ntotal) hold D = -FLT_MAX (numeric_limits<float>::lowest()), I = -1,
+ * which is FAISS's heap neutral element.  `id_offset` is added to every
+ * returned id (row-sharded multi-GPU search: global id = local row + offset).
+ * ptrs_are_device: 0 = q/D/I are host pointers (call is synchronous),
+ *                  1 = device pointers on the index's device (stream-ordered;
+ *                      the call may still synchronise internally when a query
+ *                      has to be escalated to the exact path). */
+int kirag_index_search(kirag_index_t* h, const float* q, int64_t nq, int k,
+                       float* D, int64_t* I, int ptrs_are_device, int64_t id_offset, void* stream);
+
+/* Same, with an explicit path selector and optional statistics. */
+int kirag_index_search_ex(kirag_index_t* h, const float* q, int64_t nq, int k,
+                          float* D, int64_t* I, int ptrs_are_device, int64_t id_offset,
+                          int path, kirag_search_stats_t* stats, void* stream);
+
+/* index.reconstruct_n(i0, n): copy rows [i0, i0+n) of the fp32 master out. */
+int kirag_index_reconstruct(const kirag_index_t* h, int64_t i0, int64_t n, float* out,
+                            int out_is_device, void* stream);
+
+/* faiss.write_index(index, path)            retriever/index.py:62
+ * Writes the FAISS "IxFI" flat-index container. */
+int kirag_index_save(const kirag_index_t* h, const char* path);
+
+/* faiss.read_index(path, flags)             retriever/index.py:73 */
+int kirag_index_load(const char* path, int device, kirag_index_t** out);
+
+/* Raw device pointers of the index storage (for zero-copy integration and
+ * for the benchmark's synthetic-corpus generator).  fp32 master is row-major
+ * [ntotal, d]. */
+int kirag_index_device_ptrs(const kirag_index_t* h, const float** master_f32, const void** shadow_bf16);
+
+/* Test hook: dense approximate scores of the bf16 tcgen05 scan, written to a
+ * host buffer laid out [ntotal, nq].  Used by the parity tests to check the
+ * tensor-core contraction in isolation from the top-k logic. */
+int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, float* out_host);
+
+/* Merge G per-shard results into the global top-k, (score desc, id asc).
+ * D_all: float32 [G, nq, k]; I_all: int64 [G, nq, k] (entries with id < 0 are
+ * padding).  Used after the NCCL all-gather of the row-sharded search. */
+int kirag_merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t nq, int k,
+                     float* D_out, int64_t* I_out, int ptrs_are_device, int device, void* stream);
+
+/* torch.topk(torch.matmul(Q, T.T), k, dim=1)   knowledge_graph/models.py:1532-1538
+ * One-shot search over a transient candidate matrix T [nt, d] (device or host
+ * pointers, no persistent index). */
+int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d, int k,
+                  float* D, int64_t* I, int ptrs_are_device, int device, void* stream);
+
+/* ---- embedding epilogue (replaces average_pool + F.normalize) ---------- */
+
+/* out[b,:] = normalize(pool(hidden[b], mask[b]))   retriever/encoders.py:56-58,75-76 (mean)
+ *                                                   retriever/encoders.py:115-117    (cls)
+ *                                                   retriever/e5.py:46-48,59-60      (mean, duplicate)
+ * hidden: device [B, S, H] with element strides (sb, ss, 1); mask: device
+ * [B, S] with element strides (mb, 1); out: device float32 [B, H] contiguous.
+ * normalize = x / max(||x||_2, 1e-12) (torch F.normalize eps).  If
+ * `normalize` == 0 only the pooling is applied (ContrieverEncoder tail,
+ * encoders.py:94-95).  An all-zero mask row divides by zero exactly like the
+ * reference does (nan/inf), it is not "fixed".  Stream-ordered. */
+int kirag_pool_normalize(const void* hidden, const void* mask, float* out,
+                         int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
+                         int hidden_dtype, int mask_dtype, int mode, int normalize,
+                         int device, void* stream);
+
+/* Backward of kirag_pool_normalize (mean or cls mode, normalize on or off):
+ * grad_hidden [B,S,H] contiguous, same dtype as `hidden_dtype`; `out` is the
+ * forward output, grad_out float32 [B,H].  `pooled_norm` float32 [B] is the
+ * pre-normalisation L2 norm saved by the forward (see kirag_pool_normalize_fwd_saved). */
+int kirag_pool_normalize_backward(const float* grad_out, const float* out, const float* pooled_norm,
+                                  const void* mask, void* grad_hidden,
+                                  int64_t B, int64_t S, int64_t H, int64_t mb,
+                                  int hidden_dtype, int mask_dtype, int mode, int normalize,
+                                  int device, void* stream);
+
+/* Forward that additionally writes the pre-normalisation norms (float32 [B]). */
+int kirag_pool_normalize_fwd_saved(const void* hidden, const void* mask, float* out, float* pooled_norm,
+                                   int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
+                                   int hidden_dtype, int mask_dtype, int mode, int normalize,
+                                   int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KIRAG_B200_H */

@@ -1,0 +1,746 @@
+// api.cu — the C ABI (include/kirag_b200.h) and the search orchestration.
+//
+// Boundary being replaced: the `faiss` module object used by
+// /root/reference/retriever/index.py (IndexFlatIP ctor :13,23; add :32;
+// search :47; write_index :62; read_index :73; ntotal :74,79) and the
+// matmul+topk of /root/reference/knowledge_graph/models.py:1532-1538.
+//
+// Search pipeline per query chunk (KIRAG_PATH_AUTO):
+//   1. convert queries to the bf16 swizzled block layout (+ ||q||)
+//   2. geometric levels over the (permuted) 128-row shadow tiles:
+//        tcgen05 filter scan  -> append (approx score, row) with score >= tau[q]
+//        select               -> keep the k' best, tighten tau[q]
+//   3. rescore the k' survivors from the fp32 master (canonical order)
+//   4. final sort by (score desc, id asc), write D/I, evaluate the certificate
+//   5. queries whose certificate failed (or whose buffer overflowed) are
+//      re-answered by the exact fp32 scan.
+#include "common.cuh"
+#include "../../include/kirag_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <vector>
+
+namespace kirag {
+
+static thread_local char g_err[768] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        // round up so that slowly growing requests do not reallocate every call
+        size_t want = (need + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return 1;
+        }
+        bytes = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+        if (!ok) set_error("cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(cudaGetLastError()));
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+__global__ void fill_f32_kernel(float* p, float v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+static int fill_f32(float* p, float v, int64_t n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, v, n);
+    KIRAG_LAUNCH_OK("fill_f32_kernel");
+    return 0;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int d,
+                                   float* __restrict__ dst) {
+    const int64_t r = blockIdx.x;
+    const float* s = src + (int64_t)idx[r] * d;
+    float* t = dst + r * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) t[c] = s[c];
+}
+
+}  // namespace kirag
+
+using namespace kirag;
+
+struct kirag_index {
+    int d = 0;
+    int metric = 0;
+    int device = 0;
+    int num_sms = 148;
+    int64_t ntotal = 0;
+    int64_t capacity = 0;       // rows
+    float* master = nullptr;    // [capacity, d] fp32
+    uint8_t* shadow = nullptr;  // bf16 tiles, capacity rounded up to 128 rows (null if d % 64)
+    unsigned* maxnorm2_bits = nullptr;
+    float maxnorm = 0.f;
+    // workspaces (grow-only)
+    DevBuf q_dev, D_dev, I_dev, qshadow, qnorm, cand, cnt, tau, overflow, flags, rescored;
+    DevBuf dense, stage_a, stage_b, qmap, qsel;
+};
+
+static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+static int index_grow(kirag_index* h, int64_t need_rows, cudaStream_t st) {
+    if (need_rows <= h->capacity) return 0;
+    int64_t cap = h->capacity + h->capacity / 2;
+    if (cap < need_rows) cap = need_rows;
+    cap = round_up(cap, kTileRows);
+    float* nm = nullptr;
+    uint8_t* ns = nullptr;
+    const size_t mbytes = (size_t)cap * h->d * sizeof(float);
+    cudaError_t e = cudaMalloc((void**)&nm, mbytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of the fp32 master (%zu bytes for %lld rows) failed: %s", mbytes,
+                  (long long)cap, cudaGetErrorString(e));
+        return 1;
+    }
+    const bool want_shadow = scan_tc_supported(h->d) != 0;
+    if (want_shadow) {
+        const size_t sbytes = (size_t)cap * h->d * 2;
+        e = cudaMalloc((void**)&ns, sbytes);
+        if (e != cudaSuccess) {
+            cudaFree(nm);
+            set_error("cudaMalloc of the bf16 shadow (%zu bytes) failed: %s", sbytes, cudaGetErrorString(e));
+            return 1;
+        }
+        // rows beyond ntotal in the last tile are masked by the scan, but keep them finite
+        if (cudaMemsetAsync(ns, 0, sbytes, st) != cudaSuccess) {
+            cudaFree(nm); cudaFree(ns);
+            set_error("cudaMemsetAsync(shadow) failed");
+            return 1;
+        }
+    }
+    if (h->ntotal > 0) {
+        cudaError_t e1 = cudaMemcpyAsync(nm, h->master, (size_t)h->ntotal * h->d * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, st);
+        cudaError_t e2 = cudaSuccess;
+        if (want_shadow && h->shadow) {
+            // copy whole tiles; the partial last tile is copied too (overwrites the zeros)
+            e2 = cudaMemcpyAsync(ns, h->shadow, (size_t)round_up(h->ntotal, kTileRows) * h->d * 2,
+                                 cudaMemcpyDeviceToDevice, st);
+        }
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            cudaFree(nm); if (ns) cudaFree(ns);
+            set_error("device copy while growing the index failed");
+            return 1;
+        }
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaFree(nm); if (ns) cudaFree(ns);
+        set_error("stream sync while growing the index failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    if (h->master) cudaFree(h->master);
+    if (h->shadow) cudaFree(h->shadow);
+    h->master = nm;
+    h->shadow = ns;
+    h->capacity = cap;
+    return 0;
+}
+
+// ------------------------------------------------------------ exact path ----
+// Answers queries qsub[0..nsub) (device, contiguous [nsub, d]) with the exact
+// fp32 scan.  Output row of query i is out_row0 + i, or qmap_dev[i] if given.
+static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, float* D, int64_t* I,
+                        int64_t out_row0, const int* qmap_dev, int64_t id_offset, cudaStream_t st) {
+    const int64_t n = h->ntotal;
+    const int d = h->d;
+    const int m = (int)((k < n) ? k : n);  // at most n real results
+    const int64_t ld = round_up(n, 32);
+    if (h->dense.ensure((size_t)kExactNQ * ld * sizeof(float))) return 1;
+    const int64_t n_seg = (n + kSelectSeg - 1) / kSelectSeg;
+    if (h->stage_a.ensure((size_t)kExactNQ * n_seg * m * sizeof(Cand))) return 1;
+    for (int64_t g0 = 0; g0 < nsub; g0 += kExactNQ) {
+        const int gq = (int)((nsub - g0 < kExactNQ) ? (nsub - g0) : kExactNQ);
+        if (launch_scan_exact(h->master, n, d, qsub + g0 * d, gq, h->dense.as<float>(), ld, h->num_sms, st)) return 1;
+        int nseg_i = 0;
+        if (launch_select_dense(h->dense.as<float>(), ld, n, gq, m, h->stage_a.as<Cand>(), &nseg_i, st)) return 1;
+        Cand* cur = h->stage_a.as<Cand>();
+        int64_t cur_stride = (int64_t)nseg_i * m;
+        int cur_count = (int)cur_stride;
+        bool use_b = true;
+        while (cur_count > kSelectSeg) {
+            const int ns2 = (cur_count + kSelectSeg - 1) / kSelectSeg;
+            DevBuf& dstb = use_b ? h->stage_b : h->stage_a;
+            // stage_a is only reused after it has been fully consumed
+            if (dstb.ensure((size_t)kExactNQ * ns2 * m * sizeof(Cand))) return 1;
+            Cand* dst = dstb.as<Cand>();
+            if (launch_select_pairs(cur, cur_stride, nullptr, cur_count, 0x7fffffff, gq, m, dst,
+                                    (int64_t)ns2 * m, ns2, nullptr, nullptr, nullptr, st)) return 1;
+            cur = dst;
+            cur_stride = (int64_t)ns2 * m;
+            cur_count = (int)cur_stride;
+            use_b = !use_b;
+        }
+        if (launch_final(cur, cur_stride, nullptr, nullptr, cur_count, cur_count, gq, k,
+                         qmap_dev ? D : D + (out_row0 + g0) * k, qmap_dev ? I : I + (out_row0 + g0) * k,
+                         id_offset, nullptr, nullptr, 0.f, 0, nullptr, nullptr,
+                         qmap_dev ? qmap_dev + g0 : nullptr, st)) return 1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------- fast path ----
+struct FastParams {
+    int kprime;
+    int cap;
+    int growth;
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v);
+}
+
+static bool fast_eligible(const kirag_index* h, int k, FastParams* fp) {
+    if (!h->shadow || !scan_tc_supported(h->d)) return false;
+    if (h->ntotal > 0x7fffff00LL) return false;
+    int64_t kp = (int64_t)4 * k;  // over-fetch k' = 4k (north_star)
+    if (kp < 32) kp = 32;
+    if (kp > 2048) return false;
+    int cap = kp <= 128 ? 2048 : 8192;
+    cap = env_int("KIRAG_CAND_CAP", cap);
+    if (cap > kSelectSeg) cap = kSelectSeg;
+    if (cap < 4 * kp) return false;
+    int growth = (int)(cap / (2 * kp));
+    if (growth > 16) growth = 16;
+    if (growth < 2) growth = 2;
+    growth = env_int("KIRAG_LEVEL_GROWTH", growth);
+    if (growth < 2) growth = 2;
+    fp->kprime = (int)kp;
+    fp->cap = cap;
+    fp->growth = growth;
+    return true;
+}
+
+static int64_t pick_tile_mult(int64_t n_tiles) {
+    // odd-ish multiplier near the golden ratio, coprime with n_tiles: consecutive
+    // positions of the tile walk land far apart, so every level is a spread-out
+    // sample of the corpus (robust against corpora sorted/clustered by position)
+    if (n_tiles <= 2) return 1;
+    int64_t m = (int64_t)(0.6180339887498949 * (double)n_tiles);
+    if (m < 1) m = 1;
+    auto gcd = [](int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; };
+    while (gcd(m, n_tiles) != 1) ++m;
+    return m % n_tiles;
+}
+
+static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float* D, int64_t* I,
+                       int64_t id_offset, const FastParams& fp, int check_cert, int* levels_out,
+                       cudaStream_t st) {
+    const int d = h->d;
+    const int64_t n = h->ntotal;
+    ScanTcPlan plan;
+    if (scan_tc_pick(nq, d, &plan)) return 1;
+    const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
+    if (h->qshadow.ensure(qs_bytes)) return 1;
+    if (h->qnorm.ensure((size_t)nq * 4)) return 1;
+    if (h->cand.ensure((size_t)nq * fp.cap * sizeof(Cand))) return 1;
+    if (h->cnt.ensure((size_t)nq * 4)) return 1;
+    const int64_t nq_pad = round_up(nq, 256);
+    if (h->tau.ensure((size_t)nq_pad * 4)) return 1;
+    if (h->overflow.ensure((size_t)nq * 4)) return 1;
+    if (h->flags.ensure((size_t)nq * 4)) return 1;
+    if (h->rescored.ensure((size_t)nq * fp.kprime * 4)) return 1;
+    KIRAG_CUDA_OK(cudaMemsetAsync(h->qshadow.p, 0, qs_bytes, st));
+    KIRAG_CUDA_OK(cudaMemsetAsync(h->cnt.p, 0, (size_t)nq * 4, st));
+    KIRAG_CUDA_OK(cudaMemsetAsync(h->overflow.p, 0, (size_t)nq * 4, st));
+    if (fill_f32(h->tau.as<float>(), INFINITY, nq_pad, st)) return 1;  // pad queries never pass
+    if (fill_f32(h->tau.as<float>(), -INFINITY, nq, st)) return 1;
+    if (launch_convert_rows(qd, nq, d, 0, h->qshadow.p, plan.bq, nullptr, h->qnorm.as<float>(), st)) return 1;
+
+    const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+    const int64_t mult = pick_tile_mult(n_tiles);
+    int64_t lo = 0;
+    int64_t hi = (fp.cap / 2) / kTileRows;
+    if (hi < 1) hi = 1;
+    if (hi > n_tiles) hi = n_tiles;
+    int levels = 0;
+    while (lo < n_tiles) {
+        if (launch_scan_tc(h->shadow, n, d, h->qshadow.p, nq, plan, lo, hi, n_tiles, mult,
+                           h->tau.as<float>(), h->cand.as<Cand>(), h->cnt.as<int>(), fp.cap, h->num_sms, st)) return 1;
+        if (launch_select_pairs(h->cand.as<Cand>(), fp.cap, h->cnt.as<int>(), 0, fp.cap, (int)nq, fp.kprime,
+                                h->cand.as<Cand>(), fp.cap, 1, h->tau.as<float>(), h->cnt.as<int>(),
+                                h->overflow.as<int>(), st)) return 1;
+        ++levels;
+        lo = hi;
+        int64_t nh = hi * fp.growth;
+        hi = (nh > n_tiles) ? n_tiles : nh;
+    }
+    if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), fp.cap, fp.kprime,
+                       h->rescored.as<float>(), nq, st)) return 1;
+    // eps bounds |approx - canonical|: bf16 rounding of both operands (2 * 2^-9, plus
+    // the cross term) and fp32 accumulation slack, times ||q|| * max_j ||x_j||
+    const float eps_factor = (float)((ldexp(1.0, -8) * 1.002 + (double)d * ldexp(1.0, -21)) * (double)h->maxnorm);
+    if (launch_final(h->cand.as<Cand>(), fp.cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, fp.kprime,
+                     (int)nq, k, D, I, id_offset, h->tau.as<float>(), h->qnorm.as<float>(), eps_factor,
+                     check_cert, h->overflow.as<int>(), h->flags.as<int>(), nullptr, st)) return 1;
+    if (levels_out) *levels_out = levels;
+    return 0;
+}
+
+static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                       int ptrs_are_device, int64_t id_offset, int path, kirag_search_stats_t* stats,
+                       cudaStream_t st) {
+    KIRAG_CHECK(h != nullptr, "search: null index");
+    KIRAG_CHECK(k > 0, "search: k must be positive (got %d)", k);
+    KIRAG_CHECK(k <= 2048, "search: k=%d exceeds the supported maximum of 2048", k);
+    KIRAG_CHECK(nq >= 0, "search: negative nq");
+    KIRAG_CHECK(path >= 0 && path <= 2, "search: unknown path %d", path);
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (nq == 0) return 0;
+    KIRAG_CHECK(q && D && I, "search: null buffer");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    const long long launches0 = g_launches.load();
+    const int d = h->d;
+    const int64_t kQChunk = 16384;
+    int64_t n_fast = 0, n_exact = 0, n_cert_fail = 0, n_overflow = 0;
+    int levels = 0;
+    FastParams fp{};
+    const bool fast_ok = (path != KIRAG_PATH_EXACT) && h->ntotal > 0 && fast_eligible(h, k, &fp);
+
+    for (int64_t q0 = 0; q0 < nq; q0 += kQChunk) {
+        const int64_t cq = (nq - q0 < kQChunk) ? (nq - q0) : kQChunk;
+        const float* qd;
+        float* Dd;
+        int64_t* Id;
+        if (ptrs_are_device) {
+            qd = q + q0 * d; Dd = D + q0 * k; Id = I + q0 * k;
+        } else {
+            if (h->q_dev.ensure((size_t)cq * d * 4)) return 1;
+            if (h->D_dev.ensure((size_t)cq * k * 4)) return 1;
+            if (h->I_dev.ensure((size_t)cq * k * 8)) return 1;
+            KIRAG_CUDA_OK(cudaMemcpyAsync(h->q_dev.p, q + q0 * d, (size_t)cq * d * 4, cudaMemcpyHostToDevice, st));
+            qd = h->q_dev.as<float>(); Dd = h->D_dev.as<float>(); Id = h->I_dev.as<int64_t>();
+        }
+        if (h->ntotal == 0) {
+            if (launch_fill_pad(Dd, Id, cq * k, st)) return 1;
+        } else if (!fast_ok) {
+            if (exact_search(h, qd, cq, k, Dd, Id, 0, nullptr, id_offset, st)) return 1;
+            n_exact += cq;
+        } else {
+            const int check = 1;
+            if (fast_search(h, qd, cq, k, Dd, Id, id_offset, fp, check, &levels, st)) return 1;
+            // certificate outcome
+            std::vector<int> flags((size_t)cq), ovf((size_t)cq);
+            KIRAG_CUDA_OK(cudaMemcpyAsync(flags.data(), h->flags.p, (size_t)cq * 4, cudaMemcpyDeviceToHost, st));
+            KIRAG_CUDA_OK(cudaMemcpyAsync(ovf.data(), h->overflow.p, (size_t)cq * 4, cudaMemcpyDeviceToHost, st));
+            KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+            std::vector<int> bad;
+            for (int64_t i = 0; i < cq; ++i) {
+                if (ovf[i]) ++n_overflow;
+                if (flags[i]) { bad.push_back((int)i); if (!ovf[i]) ++n_cert_fail; }
+            }
+            if (!bad.empty() && path == KIRAG_PATH_AUTO) {
+                const int64_t nb = (int64_t)bad.size();
+                if (h->qmap.ensure((size_t)nb * 4)) return 1;
+                if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
+                KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+                gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
+                KIRAG_LAUNCH_OK("gather_rows_kernel");
+                if (exact_search(h, h->qsel.as<float>(), nb, k, Dd, Id, 0, h->qmap.as<int>(), id_offset, st)) return 1;
+                // bad[] lives on the host stack frame until the copy above has been consumed
+                KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+                n_exact += nb;
+                n_fast += cq - nb;
+            } else {
+                n_fast += cq;
+            }
+        }
+        if (!ptrs_are_device) {
+            KIRAG_CUDA_OK(cudaMemcpyAsync(D + q0 * k, Dd, (size_t)cq * k * 4, cudaMemcpyDeviceToHost, st));
+            KIRAG_CUDA_OK(cudaMemcpyAsync(I + q0 * k, Id, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, st));
+            KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+        }
+    }
+    if (stats) {
+        stats->nq = nq;
+        stats->n_fast = n_fast;
+        stats->n_exact = n_exact;
+        stats->n_cert_fail = n_cert_fail;
+        stats->n_overflow = n_overflow;
+        stats->levels = levels;
+        stats->path = fast_ok ? path : KIRAG_PATH_EXACT;
+        stats->kernel_launches = g_launches.load() - launches0;
+    }
+    return 0;
+}
+
+// ================================================================= C ABI ====
+extern "C" {
+
+int kirag_abi_version(void) { return KIRAG_ABI_VERSION; }
+
+const char* kirag_last_error(void) { return g_err; }
+
+int kirag_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int kirag_index_create(int d, int metric, int device, kirag_index_t** out) {
+    KIRAG_CHECK(out != nullptr, "index_create: null out pointer");
+    *out = nullptr;
+    KIRAG_CHECK(d > 0 && d <= 16384, "index_create: unsupported dimension %d", d);
+    KIRAG_CHECK(metric == KIRAG_METRIC_INNER_PRODUCT,
+                "index_create: only the inner-product metric is implemented (got %d)", metric);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("index_create: no CUDA device available (%s); this library has no CPU path",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return 1;
+    }
+    KIRAG_CHECK(device >= 0 && device < ndev, "index_create: device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    KIRAG_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    KIRAG_CHECK(prop.major == 10, "index_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    kirag_index* h = new (std::nothrow) kirag_index();
+    KIRAG_CHECK(h != nullptr, "index_create: out of host memory");
+    h->d = d;
+    h->metric = metric;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    if (cudaMalloc((void**)&h->maxnorm2_bits, 4) != cudaSuccess || cudaMemset(h->maxnorm2_bits, 0, 4) != cudaSuccess) {
+        set_error("index_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+int kirag_index_destroy(kirag_index_t* h) {
+    if (!h) return 0;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    if (h->master) cudaFree(h->master);
+    if (h->shadow) cudaFree(h->shadow);
+    if (h->maxnorm2_bits) cudaFree(h->maxnorm2_bits);
+    DevBuf* bufs[] = {&h->q_dev, &h->D_dev, &h->I_dev, &h->qshadow, &h->qnorm, &h->cand, &h->cnt, &h->tau,
+                      &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel};
+    for (DevBuf* b : bufs) b->release();
+    delete h;
+    return 0;
+}
+
+int kirag_index_reserve(kirag_index_t* h, int64_t n_total) {
+    KIRAG_CHECK(h != nullptr, "index_reserve: null index");
+    KIRAG_CHECK(n_total >= 0, "index_reserve: negative size");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    return index_grow(h, n_total, 0);
+}
+
+int kirag_index_add(kirag_index_t* h, const float* x, int64_t n, int x_is_device, void* stream) {
+    KIRAG_CHECK(h != nullptr, "index_add: null index");
+    KIRAG_CHECK(n >= 0, "index_add: negative n");
+    if (n == 0) return 0;
+    KIRAG_CHECK(x != nullptr, "index_add: null data");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    KIRAG_CHECK(h->ntotal + n <= 0x7fffff00LL, "index_add: more than 2^31 rows per device are not supported");
+    if (index_grow(h, h->ntotal + n, st)) return 1;
+    float* dst = h->master + h->ntotal * (int64_t)h->d;
+    KIRAG_CUDA_OK(cudaMemcpyAsync(dst, x, (size_t)n * h->d * sizeof(float),
+                                  x_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (launch_convert_rows(dst, n, h->d, h->ntotal, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, st)) return 1;
+    unsigned bits = 0;
+    KIRAG_CUDA_OK(cudaMemcpyAsync(&bits, h->maxnorm2_bits, 4, cudaMemcpyDeviceToHost, st));
+    KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+    float m2;
+    memcpy(&m2, &bits, 4);
+    h->maxnorm = sqrtf(m2);
+    h->ntotal += n;
+    return 0;
+}
+
+int64_t kirag_index_ntotal(const kirag_index_t* h) { return h ? h->ntotal : -1; }
+int kirag_index_dim(const kirag_index_t* h) { return h ? h->d : -1; }
+
+int kirag_index_search(kirag_index_t* h, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                       int ptrs_are_device, int64_t id_offset, void* stream) {
+    int path = env_int("KIRAG_PATH", KIRAG_PATH_AUTO);
+    return search_impl(h, q, nq, k, D, I, ptrs_are_device, id_offset, path, nullptr, (cudaStream_t)stream);
+}
+
+int kirag_index_search_ex(kirag_index_t* h, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                          int ptrs_are_device, int64_t id_offset, int path, kirag_search_stats_t* stats,
+                          void* stream) {
+    return search_impl(h, q, nq, k, D, I, ptrs_are_device, id_offset, path, stats, (cudaStream_t)stream);
+}
+
+int kirag_index_reconstruct(const kirag_index_t* h, int64_t i0, int64_t n, float* out, int out_is_device,
+                            void* stream) {
+    KIRAG_CHECK(h != nullptr && out != nullptr, "index_reconstruct: null argument");
+    KIRAG_CHECK(i0 >= 0 && n >= 0 && i0 + n <= h->ntotal, "index_reconstruct: rows [%lld,%lld) out of range (ntotal=%lld)",
+                (long long)i0, (long long)(i0 + n), (long long)h->ntotal);
+    if (n == 0) return 0;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    KIRAG_CUDA_OK(cudaMemcpyAsync(out, h->master + i0 * (int64_t)h->d, (size_t)n * h->d * 4,
+                                  out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!out_is_device) KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+/* debug / test hook: dense approximate (bf16 tcgen05) scores, out is host [ntotal, nq] */
+int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, float* out_host) {
+    KIRAG_CHECK(h && q_host && out_host, "debug_scores: null argument");
+    KIRAG_CHECK(h->shadow && scan_tc_supported(h->d), "debug_scores: index has no bf16 shadow (d=%d)", h->d);
+    KIRAG_CHECK(nq > 0 && h->ntotal > 0, "debug_scores: empty input");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    cudaStream_t st = 0;
+    const int d = h->d;
+    ScanTcPlan plan;
+    if (scan_tc_pick(nq, d, &plan)) return 1;
+    const char* force = getenv("KIRAG_DEBUG_BQ");
+    if (force && *force) { plan.bq = atoi(force); plan.resident = (plan.bq == 32) ? 1 : 0; }
+    const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
+    const int64_t nq_pad = round_up(nq, 256);
+    DevBuf qd, qs, tau, cnt, dump;
+    int rc = 1;
+    do {
+        if (qd.ensure((size_t)nq * d * 4) || qs.ensure(qs_bytes) || tau.ensure((size_t)nq_pad * 4) ||
+            cnt.ensure((size_t)nq_pad * 4) || dump.ensure((size_t)h->ntotal * nq * 4)) break;
+        if (cudaMemcpyAsync(qd.p, q_host, (size_t)nq * d * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        if (cudaMemsetAsync(qs.p, 0, qs_bytes, st) != cudaSuccess) break;
+        if (cudaMemsetAsync(cnt.p, 0, (size_t)nq_pad * 4, st) != cudaSuccess) break;
+        if (cudaMemsetAsync(dump.p, 0, (size_t)h->ntotal * nq * 4, st) != cudaSuccess) break;
+        if (fill_f32(tau.as<float>(), INFINITY, nq_pad, st)) break;
+        if (launch_convert_rows(qd.as<float>(), nq, d, 0, qs.p, plan.bq, nullptr, nullptr, st)) break;
+        if (launch_scan_tc_dump(h->shadow, h->ntotal, d, qs.p, nq, plan, tau.as<float>(), cnt.as<int>(),
+                                dump.as<float>(), nq, h->num_sms, st)) break;
+        if (cudaMemcpyAsync(out_host, dump.p, (size_t)h->ntotal * nq * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("debug_scores: copy/sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rc = 0;
+    } while (0);
+    qd.release(); qs.release(); tau.release(); cnt.release(); dump.release();
+    return rc;
+}
+
+int kirag_index_device_ptrs(const kirag_index_t* h, const float** master_f32, const void** shadow_bf16) {
+    KIRAG_CHECK(h != nullptr, "index_device_ptrs: null index");
+    if (master_f32) *master_f32 = h->master;
+    if (shadow_bf16) *shadow_bf16 = h->shadow;
+    return 0;
+}
+
+// ---- FAISS "IxFI" container (faiss 1.8.0 index_write.cpp: write_index_header
+//      + WRITEXBVECTOR(codes)); restated from the published format -------------
+static const size_t kIoChunkRows = 65536;
+
+int kirag_index_save(const kirag_index_t* h, const char* path) {
+    KIRAG_CHECK(h != nullptr && path != nullptr, "index_save: null argument");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    FILE* f = fopen(path, "wb");
+    KIRAG_CHECK(f != nullptr, "index_save: cannot open %s for writing", path);
+    bool ok = true;
+    const uint32_t fourcc = (uint32_t)'I' | ((uint32_t)'x' << 8) | ((uint32_t)'F' << 16) | ((uint32_t)'I' << 24);
+    const int32_t d = h->d;
+    const int64_t ntotal = h->ntotal;
+    const int64_t dummy = (int64_t)1 << 20;
+    const uint8_t trained = 1;
+    const int32_t metric = 0;  // METRIC_INNER_PRODUCT
+    const uint64_t words = (uint64_t)ntotal * (uint64_t)d;
+    ok = ok && fwrite(&fourcc, 4, 1, f) == 1 && fwrite(&d, 4, 1, f) == 1 && fwrite(&ntotal, 8, 1, f) == 1 &&
+         fwrite(&dummy, 8, 1, f) == 1 && fwrite(&dummy, 8, 1, f) == 1 && fwrite(&trained, 1, 1, f) == 1 &&
+         fwrite(&metric, 4, 1, f) == 1 && fwrite(&words, 8, 1, f) == 1;
+    float* stage = nullptr;
+    const size_t chunk_bytes = kIoChunkRows * (size_t)d * 4;
+    if (ok && ntotal > 0 && cudaMallocHost((void**)&stage, chunk_bytes) != cudaSuccess) {
+        set_error("index_save: cudaMallocHost failed");
+        fclose(f);
+        return 1;
+    }
+    for (int64_t r = 0; ok && r < ntotal; r += (int64_t)kIoChunkRows) {
+        const int64_t rows = (ntotal - r < (int64_t)kIoChunkRows) ? (ntotal - r) : (int64_t)kIoChunkRows;
+        if (cudaMemcpy(stage, h->master + r * d, (size_t)rows * d * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            ok = false;
+            break;
+        }
+        ok = fwrite(stage, 4, (size_t)rows * d, f) == (size_t)rows * d;
+    }
+    if (stage) cudaFreeHost(stage);
+    if (fclose(f) != 0) ok = false;
+    KIRAG_CHECK(ok, "index_save: write to %s failed", path);
+    return 0;
+}
+
+int kirag_index_load(const char* path, int device, kirag_index_t** out) {
+    KIRAG_CHECK(path != nullptr && out != nullptr, "index_load: null argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    KIRAG_CHECK(f != nullptr, "index_load: cannot open %s", path);
+    uint32_t fourcc = 0; int32_t d = 0; int64_t ntotal = 0, dummy = 0; uint8_t trained = 0; int32_t metric = 0;
+    uint64_t words = 0;
+    bool ok = fread(&fourcc, 4, 1, f) == 1 && fread(&d, 4, 1, f) == 1 && fread(&ntotal, 8, 1, f) == 1 &&
+              fread(&dummy, 8, 1, f) == 1 && fread(&dummy, 8, 1, f) == 1 && fread(&trained, 1, 1, f) == 1 &&
+              fread(&metric, 4, 1, f) == 1;
+    const uint32_t ixfi = (uint32_t)'I' | ((uint32_t)'x' << 8) | ((uint32_t)'F' << 16) | ((uint32_t)'I' << 24);
+    if (!ok || fourcc != ixfi) {
+        fclose(f);
+        set_error("index_load: %s is not an IxFI (IndexFlatIP) file (fourcc 0x%08x)", path, fourcc);
+        return 1;
+    }
+    if (metric > 1) { float arg; ok = ok && fread(&arg, 4, 1, f) == 1; }
+    ok = ok && fread(&words, 8, 1, f) == 1;
+    if (!ok || metric != 0 || d <= 0 || ntotal < 0 || words != (uint64_t)ntotal * (uint64_t)d) {
+        fclose(f);
+        set_error("index_load: %s has an inconsistent header (d=%d ntotal=%lld metric=%d words=%llu)", path, d,
+                  (long long)ntotal, metric, (unsigned long long)words);
+        return 1;
+    }
+    kirag_index_t* h = nullptr;
+    if (kirag_index_create(d, KIRAG_METRIC_INNER_PRODUCT, device, &h)) { fclose(f); return 1; }
+    if (kirag_index_reserve(h, ntotal)) { fclose(f); kirag_index_destroy(h); return 1; }
+    std::vector<float> stage;
+    if (ntotal > 0) stage.resize(kIoChunkRows * (size_t)d);
+    for (int64_t r = 0; r < ntotal; r += (int64_t)kIoChunkRows) {
+        const int64_t rows = (ntotal - r < (int64_t)kIoChunkRows) ? (ntotal - r) : (int64_t)kIoChunkRows;
+        if (fread(stage.data(), 4, (size_t)rows * d, f) != (size_t)rows * d) {
+            fclose(f); kirag_index_destroy(h);
+            set_error("index_load: %s is truncated", path);
+            return 1;
+        }
+        if (kirag_index_add(h, stage.data(), rows, 0, nullptr)) { fclose(f); kirag_index_destroy(h); return 1; }
+    }
+    fclose(f);
+    *out = h;
+    return 0;
+}
+
+int kirag_merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t nq, int k, float* D_out,
+                     int64_t* I_out, int ptrs_are_device, int device, void* stream) {
+    KIRAG_CHECK(G > 0 && k > 0 && nq >= 0, "merge_topk: bad shape G=%d nq=%lld k=%d", G, (long long)nq, k);
+    if (nq == 0) return 0;
+    KIRAG_CHECK(D_all && I_all && D_out && I_out, "merge_topk: null buffer");
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ptrs_are_device) return launch_merge(D_all, I_all, G, nq, k, D_out, I_out, st);
+    const size_t nin = (size_t)G * nq * k, nout = (size_t)nq * k;
+    float* dD = nullptr; int64_t* dI = nullptr; float* oD = nullptr; int64_t* oI = nullptr;
+    int rc = 1;
+    do {
+        if (cudaMalloc((void**)&dD, nin * 4) != cudaSuccess || cudaMalloc((void**)&dI, nin * 8) != cudaSuccess ||
+            cudaMalloc((void**)&oD, nout * 4) != cudaSuccess || cudaMalloc((void**)&oI, nout * 8) != cudaSuccess) {
+            set_error("merge_topk: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (cudaMemcpyAsync(dD, D_all, nin * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(dI, I_all, nin * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            set_error("merge_topk: H2D copy failed");
+            break;
+        }
+        if (launch_merge(dD, dI, G, nq, k, oD, oI, st)) break;
+        if (cudaMemcpyAsync(D_out, oD, nout * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(I_out, oI, nout * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("merge_topk: D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rc = 0;
+    } while (0);
+    if (dD) cudaFree(dD); if (dI) cudaFree(dI); if (oD) cudaFree(oD); if (oI) cudaFree(oI);
+    return rc;
+}
+
+int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d, int k, float* D, int64_t* I,
+                  int ptrs_are_device, int device, void* stream) {
+    KIRAG_CHECK(nt >= 0 && nq >= 0, "topk_ip: negative size");
+    kirag_index_t* h = nullptr;
+    if (kirag_index_create(d, KIRAG_METRIC_INNER_PRODUCT, device, &h)) return 1;
+    int rc = 0;
+    if (nt > 0) rc = kirag_index_add(h, t, nt, ptrs_are_device, stream);
+    if (!rc) rc = kirag_index_search(h, q, nq, k, D, I, ptrs_are_device, 0, stream);
+    if (!rc && ptrs_are_device) {
+        DeviceGuard guard(device);
+        if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+            set_error("topk_ip: stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = 1;
+        }
+    }
+    kirag_index_destroy(h);
+    return rc;
+}
+
+int kirag_pool_normalize(const void* hidden, const void* mask, float* out, int64_t B, int64_t S, int64_t H,
+                         int64_t sb, int64_t ss, int64_t mb, int hidden_dtype, int mask_dtype, int mode,
+                         int normalize, int device, void* stream) {
+    KIRAG_CHECK(hidden && out, "pool_normalize: null buffer");
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    return launch_pool_normalize(hidden, mask, out, nullptr, B, S, H, sb, ss, mb, hidden_dtype, mask_dtype, mode,
+                                 normalize, (cudaStream_t)stream);
+}
+
+int kirag_pool_normalize_fwd_saved(const void* hidden, const void* mask, float* out, float* pooled_norm,
+                                   int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
+                                   int hidden_dtype, int mask_dtype, int mode, int normalize, int device,
+                                   void* stream) {
+    KIRAG_CHECK(hidden && out && pooled_norm, "pool_normalize_fwd_saved: null buffer");
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    return launch_pool_normalize(hidden, mask, out, pooled_norm, B, S, H, sb, ss, mb, hidden_dtype, mask_dtype,
+                                 mode, normalize, (cudaStream_t)stream);
+}
+
+int kirag_pool_normalize_backward(const float* grad_out, const float* out, const float* pooled_norm,
+                                  const void* mask, void* grad_hidden, int64_t B, int64_t S, int64_t H,
+                                  int64_t mb, int hidden_dtype, int mask_dtype, int mode, int normalize,
+                                  int device, void* stream) {
+    KIRAG_CHECK(grad_out && out && pooled_norm && grad_hidden, "pool_normalize_backward: null buffer");
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    return launch_pool_normalize_backward(grad_out, out, pooled_norm, mask, grad_hidden, B, S, H, mb, hidden_dtype,
+                                          mask_dtype, mode, normalize, (cudaStream_t)stream);
+}
+
+}  // extern "C"

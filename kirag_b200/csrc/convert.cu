@@ -1,0 +1,102 @@
+// convert.cu — fp32 rows -> bf16 shadow in the swizzled block layout, plus
+// the row norms the exactness certificate needs.
+//
+// Replaces the storage half of faiss.IndexFlatIP.add (reference call site
+// /root/reference/retriever/index.py:32): FAISS appends the fp32 rows to its
+// code vector; this build keeps the same fp32 master and additionally writes
+// a bf16 shadow that the tcgen05 filter scan streams.
+#include "common.cuh"
+
+namespace kirag {
+
+// One warp per row.  Lane l handles 16-byte output granules l, l+32, ... (8
+// columns each): reads 32 contiguous bytes of fp32, writes 16 bytes of bf16.
+// A warp therefore reads 1 KB contiguous per step and fills whole 128-byte
+// swizzle rows.  HBM-bound: 4 B read + 2 B written per element.
+__global__ void __launch_bounds__(256)
+convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_t dst_row0,
+                    uint8_t* __restrict__ shadow, int rows_per_tile,
+                    unsigned* __restrict__ maxnorm2_bits, float* __restrict__ row_norms) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n_gran = d >> 3;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        const float* row = src + r * (int64_t)d;
+        float ss = 0.0f;
+        for (int g = lane; g < n_gran; g += 32) {
+            const float4 a = *reinterpret_cast<const float4*>(row + g * 8);
+            const float4 b = *reinterpret_cast<const float4*>(row + g * 8 + 4);
+            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss);
+            ss = fmaf(a.z, a.z, ss); ss = fmaf(a.w, a.w, ss);
+            ss = fmaf(b.x, b.x, ss); ss = fmaf(b.y, b.y, ss);
+            ss = fmaf(b.z, b.z, ss); ss = fmaf(b.w, b.w, ss);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(a.z, a.w);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(b.z, b.w);
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&p0);
+            o.y = *reinterpret_cast<uint32_t*>(&p1);
+            o.z = *reinterpret_cast<uint32_t*>(&p2);
+            o.w = *reinterpret_cast<uint32_t*>(&p3);
+            const size_t off = shadow_offset(dst_row0 + r, g * 8, d, rows_per_tile);
+            *reinterpret_cast<uint4*>(shadow + off) = o;
+        }
+        ss = warp_butterfly_sum(ss);
+        if (lane == 0) {
+            if (row_norms) row_norms[r] = sqrtf(ss);
+            // non-negative floats order like their bit patterns; NaN/inf norms
+            // saturate the bound (certificate then always fails -> exact path)
+            if (maxnorm2_bits) {
+                unsigned bits = (ss == ss) ? __float_as_uint(ss) : 0x7f800000u;
+                atomicMax(maxnorm2_bits, bits);
+            }
+        }
+    }
+}
+
+// Row norms only (d not a multiple of 64: no shadow, exact path only).
+__global__ void __launch_bounds__(256)
+row_norms_kernel(const float* __restrict__ src, int64_t n_rows, int d,
+                 unsigned* __restrict__ maxnorm2_bits, float* __restrict__ row_norms) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_rows; r += n_warps) {
+        const float* row = src + r * (int64_t)d;
+        float ss = 0.0f;
+        for (int c = lane; c < d; c += 32) ss = fmaf(row[c], row[c], ss);
+        ss = warp_butterfly_sum(ss);
+        if (lane == 0) {
+            if (row_norms) row_norms[r] = sqrtf(ss);
+            if (maxnorm2_bits) {
+                unsigned bits = (ss == ss) ? __float_as_uint(ss) : 0x7f800000u;
+                atomicMax(maxnorm2_bits, bits);
+            }
+        }
+    }
+}
+
+int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row0, void* shadow,
+                        int rows_per_tile, unsigned* maxnorm2_bits, float* row_norms,
+                        cudaStream_t st) {
+    if (n_rows <= 0) return 0;
+    const int threads = 256;
+    const int64_t warps_needed = n_rows;
+    int64_t blocks = (warps_needed * 32 + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride, 16 CTAs per SM
+    if (shadow) {
+        KIRAG_CHECK(d % 64 == 0, "convert: d=%d is not a multiple of 64", d);
+        convert_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+            src, n_rows, d, dst_row0, (uint8_t*)shadow, rows_per_tile, maxnorm2_bits, row_norms);
+        KIRAG_LAUNCH_OK("convert_rows_kernel");
+    } else {
+        row_norms_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, n_rows, d, maxnorm2_bits,
+                                                              row_norms);
+        KIRAG_LAUNCH_OK("row_norms_kernel");
+    }
+    return 0;
+}
+
+}  // namespace kirag

@@ -1,0 +1,337 @@
+// select.cu — top-m selection by (score descending, id ascending).
+//
+// FAISS keeps a per-query heap (k < 100) or reservoir (k >= 100) while it
+// scans (the code behind faiss.IndexFlatIP.search, reference call site
+// /root/reference/retriever/index.py:47).  Here selection is a separate,
+// small stage: every list that has to be reduced — a 8192-row segment of
+// dense exact scores, a query's candidate buffer after a filter level, the
+// rescored candidates, the all-gathered per-shard results — is sorted by one
+// CTA in shared memory with a bitonic network over 64-bit items whose integer
+// order IS the (score desc, id asc) total order (common.cuh: pack_item).
+// Lists are at most 8192 items (64 KB of shared memory).
+#include "common.cuh"
+
+namespace kirag {
+
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* s, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int pos = 2 * t - (t & (stride - 1));
+                const int par = pos + stride;
+                const bool desc = ((pos & size) == 0);
+                const uint64_t a = s[pos], b = s[par];
+                if ((a < b) == desc) { s[pos] = b; s[par] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ---- dense exact scores -> per-segment top-m --------------------------------
+// grid (n_seg, nq); scores[q*ld + row]; out[(q*n_seg + seg)*m + j]
+__global__ void __launch_bounds__(1024)
+select_dense_kernel(const float* __restrict__ scores, int64_t ld, int64_t n, int m,
+                    Cand* __restrict__ out) {
+    extern __shared__ uint64_t items[];
+    const int seg = blockIdx.x, q = blockIdx.y, n_seg = gridDim.x;
+    const int64_t lo = (int64_t)seg * kSelectSeg;
+    const int len = (int)((n - lo < kSelectSeg) ? (n - lo) : kSelectSeg);
+    const int P = next_pow2(len);
+    const float* src = scores + (int64_t)q * ld + lo;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        items[i] = (i < len) ? pack_item(src[i], (int32_t)(lo + i)) : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(items, P);
+    Cand* dst = out + ((int64_t)q * n_seg + seg) * m;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        Cand c;
+        if (j < P && item_key(items[j]) != 0u) {
+            c.s = key_score(item_key(items[j]));
+            c.id = item_id(items[j]);
+        } else {
+            c.s = __int_as_float(0x7fc00000);
+            c.id = -1;
+        }
+        dst[j] = c;
+    }
+}
+
+// ---- candidate lists -> per-segment top-m ------------------------------------
+// grid (n_seg, nq).  When n_seg == 1 this is also the between-level compaction
+// of the filter path: it tightens tau[q] to the m-th best approximate score,
+// resets the append counter and records buffer overflow.
+__global__ void __launch_bounds__(1024)
+select_pairs_kernel(const Cand* __restrict__ in, int64_t in_stride, const int* __restrict__ cnt,
+                    int fixed_count, int cap, int m, Cand* __restrict__ out, int64_t out_stride,
+                    float* __restrict__ tau, int* __restrict__ cnt_out, int* __restrict__ overflow) {
+    extern __shared__ uint64_t items[];
+    const int seg = blockIdx.x, q = blockIdx.y, n_seg = gridDim.x;
+    int raw = cnt ? cnt[q] : fixed_count;
+    int count = raw > cap ? cap : raw;
+    const int lo = seg * kSelectSeg;
+    int len = count - lo;
+    if (len > kSelectSeg) len = kSelectSeg;
+    if (len < 0) len = 0;
+    const int P = next_pow2(len > m ? len : m);
+    const Cand* src = in + (int64_t)q * in_stride + lo;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t it = 0ull;
+        if (i < len) {
+            const Cand c = src[i];
+            if (c.id >= 0) it = pack_item(c.s, c.id);
+        }
+        items[i] = it;
+    }
+    __syncthreads();
+    // a list that already fits needs no sort unless it is the last reduction
+    bitonic_sort_desc(items, P);
+    Cand* dst = out + (int64_t)q * out_stride + (int64_t)seg * m;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        Cand c;
+        if (item_key(items[j]) != 0u) {
+            c.s = key_score(item_key(items[j]));
+            c.id = item_id(items[j]);
+        } else {
+            c.s = __int_as_float(0x7fc00000);
+            c.id = -1;
+        }
+        dst[j] = c;
+    }
+    if (threadIdx.x == 0 && n_seg == 1) {
+        // number of valid items kept
+        int kept = len < m ? len : m;
+        // items with key 0 (NaN scores / empty) sort last; count the valid prefix
+        // by binary search over the sorted keys
+        int a = 0, b = kept;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (item_key(items[mid]) != 0u) a = mid + 1; else b = mid;
+        }
+        kept = a;
+        if (cnt_out) cnt_out[q] = kept;
+        if (tau && kept >= m) tau[q] = key_score(item_key(items[m - 1]));
+        if (overflow && raw > cap) overflow[q] = 1;
+    }
+}
+
+// ---- rescored candidates -> D, I (+ certificate) -----------------------------
+// grid nq.  Sorts the (canonical fp32 score, row) pairs, writes the first k as
+// the result row and checks the exactness certificate:
+//   every row that is NOT a candidate has approximate score <= tau[q]; its
+//   canonical score is therefore <= tau[q] + eps with eps = eps_factor *
+//   ||q|| (eps_factor already contains max_j ||x_j||).  If the k-th canonical
+//   score exceeds tau[q] + eps, no dropped row can enter the top-k.
+__global__ void __launch_bounds__(1024)
+final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __restrict__ rescored,
+             const int* __restrict__ cnt, int fixed_count, int m_in, int k, float* __restrict__ D,
+             int64_t* __restrict__ I, int64_t id_offset, const float* __restrict__ tau,
+             const float* __restrict__ qnorm, float eps_factor, int check_cert,
+             const int* __restrict__ overflow, int* __restrict__ flags,
+             const int* __restrict__ qmap) {
+    extern __shared__ uint64_t items[];
+    const int q = blockIdx.x;
+    int count = cnt ? cnt[q] : fixed_count;
+    if (count > m_in) count = m_in;
+    const int P = next_pow2(count > 0 ? count : 1);
+    const Cand* src = cand + (int64_t)q * cand_stride;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t it = 0ull;
+        if (i < count) {
+            const int32_t id = src[i].id;
+            const float s = rescored ? rescored[(int64_t)q * m_in + i] : src[i].s;
+            if (id >= 0) it = pack_item(s, id);
+        }
+        items[i] = it;
+    }
+    __syncthreads();
+    bitonic_sort_desc(items, P);
+    const int64_t qo = qmap ? qmap[q] : q;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        float s = -FLT_MAX;
+        int64_t id = -1;
+        if (j < P && item_key(items[j]) != 0u) {
+            s = key_score(item_key(items[j]));
+            id = (int64_t)item_id(items[j]) + id_offset;
+        }
+        D[qo * k + j] = s;
+        I[qo * k + j] = id;
+    }
+    if (threadIdx.x == 0 && flags) {
+        int fail = 0;
+        if (overflow && overflow[q]) fail = 1;
+        if (check_cert && tau) {
+            const float t = tau[q];
+            if (t > -INFINITY) {
+                // something may have been dropped: need k valid results whose
+                // k-th score clears the dropped bound
+                if (k > P || item_key(items[k - 1]) == 0u) {
+                    fail = 1;
+                } else {
+                    const float kth = key_score(item_key(items[k - 1]));
+                    const float eps = eps_factor * qnorm[q];
+                    if (!(kth - eps > t)) fail = 1;
+                }
+            }
+        }
+        flags[q] = fail;
+    }
+}
+
+// ---- multi-GPU merge ---------------------------------------------------------
+// grid nq.  G*k (score, int64 id) pairs -> top-k by (score desc, id asc).
+__device__ __forceinline__ bool kv_before(uint32_t ka, int64_t ia, uint32_t kb, int64_t ib) {
+    return (ka > kb) || (ka == kb && ia < ib);
+}
+
+__global__ void __launch_bounds__(1024)
+merge_kernel(const float* __restrict__ D_all, const int64_t* __restrict__ I_all, int G, int64_t nq,
+             int k, float* __restrict__ D_out, int64_t* __restrict__ I_out, int P) {
+    extern __shared__ uint64_t smem_raw[];
+    int64_t* ids = reinterpret_cast<int64_t*>(smem_raw);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ids + P);
+    const int64_t q = blockIdx.x;
+    const int L = G * k;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint32_t key = 0u;
+        int64_t id = INT64_MAX;
+        if (i < L) {
+            const int g = i / k, j = i - g * k;
+            const int64_t src = ((int64_t)g * nq + q) * k + j;
+            const int64_t v = I_all[src];
+            if (v >= 0) { key = score_key(D_all[src]); id = v; }
+            if (key == 0u) id = INT64_MAX;
+        }
+        keys[i] = key;
+        ids[i] = id;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int pos = 2 * t - (t & (stride - 1));
+                const int par = pos + stride;
+                const bool desc = ((pos & size) == 0);
+                const uint32_t ka = keys[pos], kb = keys[par];
+                const int64_t ia = ids[pos], ib = ids[par];
+                // in a descending run the element that comes "before" goes first
+                const bool b_first = kv_before(kb, ib, ka, ia);
+                if (b_first == desc && !(ka == kb && ia == ib)) {
+                    keys[pos] = kb; keys[par] = ka;
+                    ids[pos] = ib; ids[par] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        float s = -FLT_MAX;
+        int64_t id = -1;
+        if (j < P && keys[j] != 0u) { s = key_score(keys[j]); id = ids[j]; }
+        D_out[q * k + j] = s;
+        I_out[q * k + j] = id;
+    }
+}
+
+__global__ void fill_pad_kernel(float* __restrict__ D, int64_t* __restrict__ I, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { D[i] = -FLT_MAX; I[i] = -1; }
+}
+
+// ------------------------------------------------------------------ hosts ----
+static int host_pow2(int v) {
+    int p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+static int sort_threads(int P) {
+    int t = P / 2;
+    if (t > 1024) t = 1024;
+    if (t < 32) t = 32;
+    return t;
+}
+
+template <typename K>
+static int ensure_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        KIRAG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)bytes));
+    }
+    return 0;
+}
+
+int launch_select_dense(const float* scores, int64_t ld, int64_t n, int nq, int m, Cand* out,
+                        int* n_seg_out, cudaStream_t st) {
+    const int64_t n_seg = (n + kSelectSeg - 1) / kSelectSeg;
+    KIRAG_CHECK(n_seg > 0 && n_seg < 0x7fffffffLL && nq > 0 && nq <= 65535,
+                "select_dense: bad grid (n_seg=%lld nq=%d)", (long long)n_seg, nq);
+    KIRAG_CHECK(m <= kSelectSeg, "select_dense: m=%d > %d", m, kSelectSeg);
+    const int P = host_pow2((int)((n < kSelectSeg) ? n : kSelectSeg));
+    const size_t smem = (size_t)P * 8;
+    if (ensure_smem(select_dense_kernel, (size_t)kSelectSeg * 8)) return 1;
+    dim3 grid((unsigned)n_seg, (unsigned)nq);
+    select_dense_kernel<<<grid, sort_threads(P), smem, st>>>(scores, ld, n, m, out);
+    KIRAG_LAUNCH_OK("select_dense_kernel");
+    if (n_seg_out) *n_seg_out = (int)n_seg;
+    return 0;
+}
+
+int launch_select_pairs(const Cand* in, int64_t in_stride, const int* cnt, int fixed_count, int cap,
+                        int nq, int m, Cand* out, int64_t out_stride, int n_seg, float* tau,
+                        int* cnt_out, int* overflow, cudaStream_t st) {
+    KIRAG_CHECK(nq > 0 && nq <= 65535 && n_seg > 0, "select_pairs: bad grid (n_seg=%d nq=%d)", n_seg, nq);
+    KIRAG_CHECK(m <= kSelectSeg, "select_pairs: m=%d > %d", m, kSelectSeg);
+    int longest = cap < kSelectSeg ? cap : kSelectSeg;
+    if (longest < m) longest = m;
+    const int P = host_pow2(longest);
+    const size_t smem = (size_t)P * 8;
+    if (ensure_smem(select_pairs_kernel, (size_t)kSelectSeg * 8)) return 1;
+    dim3 grid((unsigned)n_seg, (unsigned)nq);
+    select_pairs_kernel<<<grid, sort_threads(P), smem, st>>>(in, in_stride, cnt, fixed_count, cap, m,
+                                                            out, out_stride, tau, cnt_out, overflow);
+    KIRAG_LAUNCH_OK("select_pairs_kernel");
+    return 0;
+}
+
+int launch_final(const Cand* cand, int64_t cand_stride, const float* rescored, const int* cnt,
+                 int fixed_count, int m_in, int nq, int k, float* D, int64_t* I, int64_t id_offset,
+                 const float* tau, const float* qnorm, float eps_factor, int check_cert,
+                 const int* overflow, int* flags, const int* qmap, cudaStream_t st) {
+    KIRAG_CHECK(m_in <= kSelectSeg, "final: m_in=%d > %d", m_in, kSelectSeg);
+    const int P = host_pow2(m_in);
+    const size_t smem = (size_t)P * 8;
+    if (ensure_smem(final_kernel, (size_t)kSelectSeg * 8)) return 1;
+    final_kernel<<<(unsigned)nq, sort_threads(P), smem, st>>>(
+        cand, cand_stride, rescored, cnt, fixed_count, m_in, k, D, I, id_offset, tau, qnorm,
+        eps_factor, check_cert, overflow, flags, qmap);
+    KIRAG_LAUNCH_OK("final_kernel");
+    return 0;
+}
+
+int launch_merge(const float* D_all, const int64_t* I_all, int G, int64_t nq, int k, float* D_out,
+                 int64_t* I_out, cudaStream_t st) {
+    if (nq <= 0) return 0;
+    const int64_t L = (int64_t)G * k;
+    KIRAG_CHECK(L <= kSelectSeg, "merge: G*k=%lld exceeds %d", (long long)L, kSelectSeg);
+    const int P = host_pow2((int)L);
+    const size_t smem = (size_t)P * 12;
+    if (ensure_smem(merge_kernel, (size_t)kSelectSeg * 12)) return 1;
+    merge_kernel<<<(unsigned)nq, sort_threads(P), smem, st>>>(D_all, I_all, G, nq, k, D_out, I_out, P);
+    KIRAG_LAUNCH_OK("merge_kernel");
+    return 0;
+}
+
+int launch_fill_pad(float* D, int64_t* I, int64_t n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    fill_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(D, I, n);
+    KIRAG_LAUNCH_OK("fill_pad_kernel");
+    return 0;
+}
+
+}  // namespace kirag

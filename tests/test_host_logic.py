@@ -1,0 +1,98 @@
+"""Host-side logic that needs no GPU: shard ranges, embedding-file pairing, the Indexer glue, the faiss stand-in."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+
+from kirag_b200 import build_index, faiss_api
+from kirag_b200 import index as kindex
+from kirag_b200.sharded import shard_range
+from oracle import oracle
+from tests.helpers import int_corpus
+
+
+def test_shard_ranges_partition_the_rows():
+    for n in (0, 1, 7, 8, 9, 1000, 21_000_000):
+        for G in (1, 2, 4, 8):
+            spans = [shard_range(n, G, r) for r in range(G)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b and c <= d
+
+
+def test_pairing_is_exact_not_substring(tmp_path):
+    # the reference pairs "…_0_999999" with "passage_id_list_1000000_1999999" by substring
+    # (faiss_index_corpus.py:37-41); exact pairing must not
+    names = ["corpus_embeddings_0_999999.pkl", "corpus_embeddings_1000000_1999999.pkl",
+             "passage_id_list_1000000_1999999.pkl", "passage_id_list_0_999999.pkl"]
+    for n in names:
+        (tmp_path / n).write_bytes(b"x")
+    pairs = build_index.pair_embedding_files(str(tmp_path))
+    assert [(os.path.basename(a), os.path.basename(b)) for a, b in pairs] == [
+        ("corpus_embeddings_0_999999.pkl", "passage_id_list_0_999999.pkl"),
+        ("corpus_embeddings_1000000_1999999.pkl", "passage_id_list_1000000_1999999.pkl")]
+
+
+def test_pairing_survives_dotted_directories(tmp_path):
+    d = tmp_path / "e5.large.v2"
+    d.mkdir()
+    (d / "corpus_embeddings_0_9.pkl").write_bytes(b"x")
+    (d / "passage_id_list_0_9.pkl").write_bytes(b"x")
+    assert len(build_index.pair_embedding_files(str(d))) == 1
+
+
+def test_faiss_stand_in_exposes_what_index_py_names():
+    import kirag_b200.as_faiss as af
+
+    mod = af.make_module()
+    for name in ("IndexFlatIP", "IndexFlatL2", "IndexPQ", "METRIC_INNER_PRODUCT", "IO_FLAG_MMAP", "write_index",
+                 "read_index"):
+        assert hasattr(mod, name)
+    with pytest.raises(NotImplementedError):
+        mod.IndexFlatL2(8)
+    with pytest.raises(NotImplementedError):
+        mod.IndexPQ(8, 2, 8, mod.METRIC_INNER_PRODUCT)
+
+
+class _OracleBackedIndex(oracle.OracleIndexFlatIP):
+    """Test double: stands in for the CUDA index so the Indexer glue can run on CPU."""
+
+
+def test_indexer_mirror_glue_on_a_test_double(tmp_path, monkeypatch):
+    monkeypatch.setitem(kindex.FAISSINDEX_DICT, "inner_product", _OracleBackedIndex)
+    monkeypatch.setattr(faiss_api, "write_index", oracle._write_index)
+    monkeypatch.setattr(faiss_api, "read_index", oracle._read_index)
+    rng = np.random.default_rng(1)
+    xb, xq = int_corpus(rng, 40, 16), int_corpus(rng, 3, 16)
+    ids = [str(1000 + 3 * i) for i in range(40)]
+    ix = kindex.Indexer(16)
+    ix.index_data(ids[:25], xb[:25].astype(np.float64))  # any float dtype, like index.py:29
+    ix.index_data(ids[25:], xb[25:])
+    res = ix.search_knn(xq, 5, index_batch_size=2, verbose=False)
+    D, I = oracle.flat_ip_search(xb, xq, 5)
+    assert len(res) == 3
+    for r, (db_ids, scores) in enumerate(res):
+        assert db_ids == [str(1000 + 3 * i) for i in I[r]] and all(isinstance(s, str) for s in db_ids)
+        assert np.array_equal(scores, D[r])
+    ix.serialize(str(tmp_path))
+    ix2 = kindex.Indexer(16)
+    ix2.deserialize_from(str(tmp_path))
+    assert ix2.index.ntotal == 40 and np.array_equal(ix2.index_id_to_db_id, ix.index_id_to_db_id)
+    # k > ntotal: -1 padding maps to the LAST id, exactly as the reference's index_id_to_db_id[-1] does
+    res = ix.search_knn(xq[:1], 45, verbose=False)
+    assert res[0][0][-1] == ids[-1]
+
+
+def test_ixfi_container_layout(tmp_path):
+    idx = oracle.OracleIndexFlatIP(4)
+    idx.add(np.arange(12, dtype=np.float32).reshape(3, 4))
+    p = tmp_path / "index.faiss"
+    oracle._write_index(idx, str(p))
+    raw = p.read_bytes()
+    assert raw[:4] == b"IxFI" and len(raw) == 45 + 3 * 4 * 4
+    assert int.from_bytes(raw[4:8], "little") == 4 and int.from_bytes(raw[8:16], "little") == 3
+    assert int.from_bytes(raw[16:24], "little") == 1 << 20 and raw[32] == 1
+    assert int.from_bytes(raw[33:37], "little") == 0 and int.from_bytes(raw[37:45], "little") == 12
+    assert np.array_equal(np.frombuffer(raw[45:], dtype="<f4"), np.arange(12, dtype=np.float32))

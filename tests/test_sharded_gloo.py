@@ -1,0 +1,67 @@
+"""world_size-2 gloo test of the sharded-search plumbing (shard ranges, global ids, gather layout, merge call).
+
+The CUDA local search and merge kernel are replaced by oracle-backed test doubles here; the real
+kernels are covered by tests/test_sharded_gpu.py.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle
+from tests.helpers import int_corpus
+
+
+class _LocalOracleIndex:
+    def __init__(self, d):
+        self.d = d
+        self.x = np.empty((0, d), dtype=np.float32)
+
+    @property
+    def ntotal(self):
+        return self.x.shape[0]
+
+    def add(self, x):
+        self.x = np.concatenate([self.x, np.asarray(x, dtype=np.float32)])
+
+    def search_device(self, q, k, id_offset=0):
+        D, I = oracle.flat_ip_search(self.x, q.numpy(), k, id_offset=id_offset)
+        return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def _merge(D_all, I_all):
+    D, I = oracle.merge_topk(D_all.numpy(), I_all.numpy())
+    return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def _worker(rank, world, port, n, d, nq, k, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kirag_b200.sharded import ShardedFlatIP
+
+        rng = np.random.default_rng(11)
+        xb, xq = int_corpus(rng, n, d), int_corpus(rng, nq, d)
+        sh = ShardedFlatIP(d, n, local_index=_LocalOracleIndex(d), merge_fn=_merge)
+        sh.add_shard(xb[sh.lo:sh.hi])
+        D, I = sh.search(torch.from_numpy(xq), k)
+        D1, I1 = oracle.flat_ip_search(xb, xq, k)
+        ret[rank] = bool(np.array_equal(I.numpy(), I1) and np.array_equal(D.numpy(), D1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,k", [(101, 7), (3, 5)])  # second case: shards smaller than k -> padded partial results
+def test_sharded_search_world_size_2(n, k):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, port, n, 16, 4, k, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
