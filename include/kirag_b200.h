@@ -82,6 +82,14 @@ const char* kirag_last_error(void);
 /* Number of usable CUDA devices (0 if none / no driver).  Never fails. */
 int kirag_device_count(void);
 
+/* Per-kernel timing of the dominant kernel (the tcgen05 filter scan) with CUDA
+ * events recorded on the launching stream; used by bench.py for the roofline
+ * line.  enable(1) clears and starts recording, read() returns the summed
+ * duration (ms), the number of launches and the corpus rows they streamed,
+ * then clears. */
+int kirag_profile_enable(int on);
+int kirag_profile_read(double* scan_ms, int64_t* scan_launches, double* scan_rows);
+
 /* ---- flat inner-product index  (replaces faiss.IndexFlatIP) ------------ */
 
 /* faiss.IndexFlatIP(d)                      retriever/index.py:13,23 */

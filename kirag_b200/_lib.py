@@ -50,6 +50,8 @@ SIGNATURES = {
     "kirag_abi_version": (c_int, []),
     "kirag_last_error": (c_char_p, []),
     "kirag_device_count": (c_int, []),
+    "kirag_profile_enable": (c_int, [c_int]),
+    "kirag_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double)]),
     "kirag_index_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
     "kirag_index_destroy": (c_int, [c_void_p]),
     "kirag_index_reserve": (c_int, [c_void_p, c_int64]),

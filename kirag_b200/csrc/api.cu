@@ -39,6 +39,17 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Optional per-kernel timing of the dominant kernel (the tcgen05 filter scan): CUDA events
+// recorded on the launching stream around every scan launch while enabled.  bench.py uses
+// it for the roofline line; it is off by default.
+struct ScanProfile {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    double rows = 0.0;  // corpus rows streamed by the recorded launches
+    double queries = 0.0;
+};
+static ScanProfile g_prof;
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -290,8 +301,21 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     if (hi > n_tiles) hi = n_tiles;
     int levels = 0;
     while (lo < n_tiles) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (g_prof.on) {
+            KIRAG_CUDA_OK(cudaEventCreate(&e0));
+            KIRAG_CUDA_OK(cudaEventCreate(&e1));
+            KIRAG_CUDA_OK(cudaEventRecord(e0, st));
+        }
         if (launch_scan_tc(h->shadow, n, d, h->qshadow.p, nq, plan, lo, hi, n_tiles, mult,
                            h->tau.as<float>(), h->cand.as<Cand>(), h->cnt.as<int>(), fp.cap, h->num_sms, st)) return 1;
+        if (g_prof.on) {
+            KIRAG_CUDA_OK(cudaEventRecord(e1, st));
+            g_prof.ev.emplace_back(e0, e1);
+            int64_t r1 = hi * kTileRows; if (r1 > n) r1 = n;
+            g_prof.rows += (double)(r1 - lo * kTileRows);
+            g_prof.queries = (double)nq;
+        }
         if (launch_select_pairs(h->cand.as<Cand>(), fp.cap, h->cnt.as<int>(), 0, fp.cap, (int)nq, fp.kprime,
                                 h->cand.as<Cand>(), fp.cap, 1, h->tau.as<float>(), h->cnt.as<int>(),
                                 h->overflow.as<int>(), st)) return 1;
@@ -411,6 +435,31 @@ int kirag_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int kirag_profile_enable(int on) {
+    for (auto& pr : g_prof.ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    g_prof.ev.clear();
+    g_prof.rows = 0.0;
+    g_prof.on = on != 0;
+    return 0;
+}
+
+int kirag_profile_read(double* scan_ms, int64_t* scan_launches, double* scan_rows) {
+    double ms = 0.0;
+    for (auto& pr : g_prof.ev) {
+        KIRAG_CUDA_OK(cudaEventSynchronize(pr.second));
+        float t = 0.f;
+        KIRAG_CUDA_OK(cudaEventElapsedTime(&t, pr.first, pr.second));
+        ms += t;
+    }
+    if (scan_ms) *scan_ms = ms;
+    if (scan_launches) *scan_launches = (int64_t)g_prof.ev.size();
+    if (scan_rows) *scan_rows = g_prof.rows;
+    for (auto& pr : g_prof.ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    g_prof.ev.clear();
+    g_prof.rows = 0.0;
+    return 0;
 }
 
 int kirag_index_create(int d, int metric, int device, kirag_index_t** out) {

@@ -1,0 +1,86 @@
+"""The Indexer interface end to end on the GPU: our mirror, and (when a copy of the reference file is
+present) the reference's own retriever/index.py running unmodified on kirag_b200.as_faiss."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.conftest import REFERENCE, unit_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def test_indexer_mirror_on_gpu(tmp_path):
+    from kirag_b200 import Indexer
+
+    rng = np.random.default_rng(0)
+    xb, xq = unit_rows(rng, 20000, 1024), unit_rows(rng, 2100, 1024)
+    ids = [str(10 * i + 3) for i in range(20000)]
+    ix = Indexer(1024, "inner_product")
+    ix.index_data(ids[:7000], xb[:7000])
+    ix.index_data(ids[7000:], xb[7000:])
+    res = ix.search_knn(xq, 10, index_batch_size=1024, verbose=False)
+    Do, Io = oracle.flat_ip_search_blas(xb, xq, 10, use_torch=True)
+    assert len(res) == 2100
+    bad = 0
+    for r, (db_ids, scores) in enumerate(res):
+        assert len(db_ids) == 10 and isinstance(db_ids[0], str) and scores.dtype == np.float32
+        np.testing.assert_allclose(scores, Do[r], rtol=1e-5, atol=1e-6)
+        bad += db_ids != [str(10 * i + 3) for i in Io[r]]
+    assert bad <= 3  # fp32 near-tie swaps only
+    ix.serialize(str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == ["index.faiss", "index_meta.faiss"]
+    ix2 = Indexer(1024, "inner_product")
+    ix2.deserialize_from(str(tmp_path))
+    res2 = ix2.search_knn(xq[:64], 10, verbose=False)
+    assert [r[0] for r in res2] == [r[0] for r in res[:64]]
+
+
+def test_build_index_from_saved_embedding_shards(tmp_path):
+    """faiss_index_corpus.py:27-52 flow: pickled torch tensors + id lists -> index.faiss + index_meta.faiss."""
+    import pickle
+
+    import torch
+
+    from kirag_b200 import Indexer
+    from kirag_b200.build_index import build_faiss_index
+
+    rng = np.random.default_rng(1)
+    xb = unit_rows(rng, 2500, 1024)
+    for s, e in ((0, 999), (1000, 1999), (2000, 2499)):
+        pickle.dump(torch.from_numpy(xb[s:e + 1]), open(tmp_path / f"corpus_embeddings_{s}_{e}.pkl", "wb"))
+        pickle.dump([str(i) for i in range(s, e + 1)], open(tmp_path / f"passage_id_list_{s}_{e}.pkl", "wb"))
+    build_faiss_index(index_folder=str(tmp_path), embedding_size=1024)
+    assert sorted(os.listdir(tmp_path)) == ["index.faiss", "index_meta.faiss"]  # inputs deleted like the reference
+    ix = Indexer(1024)
+    ix.deserialize_from(str(tmp_path))
+    xq = unit_rows(rng, 3, 1024)
+    res = ix.search_knn(xq, 5, verbose=False)
+    Do, Io = oracle.flat_ip_search(xb, xq, 5, accum="f64")
+    assert [r[0] for r in res] == [[str(i) for i in row] for row in Io]
+
+
+def test_reference_indexer_unmodified_on_the_b200_library(tmp_path):
+    if not os.path.isdir(os.path.join(REFERENCE, "retriever")):
+        pytest.skip("/root/reference is not present on this box")
+    import kirag_b200.as_faiss as af
+
+    af.install()
+    sys.path.insert(0, REFERENCE)
+    sys.modules.pop("retriever.index", None)
+    try:
+        ref = importlib.import_module("retriever.index")
+        rng = np.random.default_rng(2)
+        xb, xq = unit_rows(rng, 5000, 1024), unit_rows(rng, 5, 1024)
+        ix = ref.Indexer(1024, "inner_product")
+        ix.index_data([str(i) for i in range(5000)], xb)
+        res = ix.search_knn(xq, 10, verbose=False)
+        Do, Io = oracle.flat_ip_search(xb, xq, 10, accum="f64")
+        assert [r[0] for r in res] == [[str(i) for i in row] for row in Io]
+    finally:
+        sys.path.remove(REFERENCE)
+        sys.modules.pop("retriever.index", None)
+        sys.modules.pop("faiss", None)

@@ -1,0 +1,312 @@
+"""Parity of the CUDA search (through the C ABI) against the oracle / fp64 ground truth.  Needs a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.conftest import unit_rows
+from tests.helpers import assert_topk_parity, exact_topk_f64, int_corpus
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+LOWEST = np.float32(-3.4028234663852886e38)
+AUTO, EXACT, FAST = 0, 1, 2
+
+
+@pytest.fixture(scope="module")
+def fa():
+    from kirag_b200 import faiss_api
+
+    assert faiss_api.get_num_gpus() >= 1, "no CUDA device: the product has no CPU path"
+    return faiss_api
+
+
+def build(fa, xb):
+    ix = fa.IndexFlatIP(xb.shape[1])
+    if len(xb):
+        ix.add(xb)
+    return ix
+
+
+def bf16_round(a):
+    """round-to-nearest-even to bf16, returned as float32 (numpy restatement of __float2bfloat16_rn)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+# ---------------------------------------------------------------- edge cases ---
+def test_hand_checkable_ties_padding_k1(fa):
+    xb = np.array([[3, 0], [1, 5], [3, 9], [0, 1], [3, -2]], dtype=np.float32)
+    xq = np.array([[1, 0]], dtype=np.float32)
+    ix = build(fa, xb)  # d=2: not a multiple of 64 -> exact path only
+    D, I = ix.search(xq, 3)
+    assert I.tolist() == [[0, 2, 4]] and D.tolist() == [[3, 3, 3]]
+    assert ix.search(xq, 2)[1].tolist() == [[0, 2]]
+    assert ix.search(xq, 1)[1].tolist() == [[0]]
+    D, I = ix.search(xq, 8)
+    assert I.tolist() == [[0, 2, 4, 1, 3, -1, -1, -1]] and np.all(D[0, 5:] == LOWEST)
+    assert ix.last_stats["n_exact"] == 1
+
+
+def test_empty_index_and_empty_queries(fa):
+    ix = fa.IndexFlatIP(64)
+    assert ix.ntotal == 0 and ix.is_trained
+    D, I = ix.search(np.ones((2, 64), dtype=np.float32), 3)
+    assert np.all(I == -1) and np.all(D == LOWEST)
+    ix.add(np.ones((3, 64), dtype=np.float32))
+    D, I = ix.search(np.zeros((0, 64), dtype=np.float32), 3)
+    assert D.shape == (0, 3) and I.shape == (0, 3)
+
+
+def test_argument_errors(fa):
+    ix = build(fa, np.ones((4, 64), dtype=np.float32))
+    with pytest.raises(AssertionError):
+        ix.search(np.ones((1, 32), dtype=np.float32), 3)
+    with pytest.raises(AssertionError):
+        ix.search(np.ones((1, 64), dtype=np.float32), 0)
+    with pytest.raises(AssertionError):
+        ix.add(np.ones((1, 63), dtype=np.float32))
+    with pytest.raises(RuntimeError):
+        ix.search(np.ones((1, 64), dtype=np.float32), 5000)  # k beyond the supported maximum
+    with pytest.raises(NotImplementedError):
+        fa.IndexFlatL2(64)
+
+
+# ------------------------------------------------------ tensor-core scores ---
+@pytest.mark.parametrize("n,d,nq", [(300, 64, 5), (1000, 128, 32), (777, 1024, 3), (4096, 1024, 40), (513, 256, 100),
+                                    (300, 192, 200)])
+def test_tcgen05_scores_match_bf16_reference(fa, n, d, nq):
+    """The MMA itself (descriptors, swizzled layout, TMEM read-out): dense approximate scores equal the
+    fp32-accumulated product of the bf16-rounded operands."""
+    rng = np.random.default_rng(n + d + nq)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    ix = build(fa, xb)
+    got = ix.debug_scores(xq)  # [n, nq]
+    ref = bf16_round(xb).astype(np.float64) @ bf16_round(xq).astype(np.float64).T
+    scale = np.linalg.norm(xb, axis=1)[:, None] * np.linalg.norm(xq, axis=1)[None, :]
+    assert got.shape == (n, nq)
+    assert np.max(np.abs(got - ref) / scale) < 2e-6  # fp32 accumulation of exact bf16 products
+
+
+def test_tcgen05_scores_exact_on_integers(fa):
+    rng = np.random.default_rng(0)
+    xb, xq = int_corpus(rng, 1500, 128), int_corpus(rng, 17, 128)
+    got = build(fa, xb).debug_scores(xq)
+    assert np.array_equal(got, (xb.astype(np.float64) @ xq.astype(np.float64).T).astype(np.float32))
+
+
+# ------------------------------------------------------------ exact path ---
+@pytest.mark.parametrize("n,d,nq,k", [(1000, 64, 5, 10), (300, 100, 3, 100), (50, 30, 4, 64), (20000, 128, 9, 7),
+                                      (9000, 1024, 6, 100), (8193, 7, 2, 2048)])
+def test_exact_path_integer_data_bit_exact(fa, n, d, nq, k):
+    rng = np.random.default_rng(n + d)
+    xb, xq = int_corpus(rng, n, d), int_corpus(rng, nq, d)
+    D, I, st = build(fa, xb).search_ex(xq, k, path=EXACT)
+    assert st["n_exact"] == nq and st["n_fast"] == 0
+    assert_topk_parity(D, I, xb, xq, k, exact=True, what="exact path")
+    Do, Io = oracle.flat_ip_search(xb, xq, k)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 96, 9, 20), (30000, 1024, 5, 100), (100, 1024, 2, 10)])
+def test_exact_path_unit_vectors(fa, n, d, nq, k):
+    rng = np.random.default_rng(n)
+    xb, xq = unit_rows(rng, n, d), unit_rows(rng, nq, d)
+    D, I, _ = build(fa, xb).search_ex(xq, k, path=EXACT)
+    assert_topk_parity(D, I, xb, xq, k, what="exact path")
+
+
+# ---------------------------------------------------------- filter (fast) path ---
+@pytest.mark.parametrize("n,d,nq,k", [(1000, 64, 5, 10), (5000, 128, 32, 10), (20000, 64, 33, 20), (70000, 128, 7, 100),
+                                      (3000, 1024, 130, 10), (40000, 256, 300, 5), (129, 64, 1, 3), (127, 64, 2, 200)])
+def test_auto_path_integer_data_bit_exact(fa, n, d, nq, k):
+    rng = np.random.default_rng(n * 3 + d)
+    xb, xq = int_corpus(rng, n, d), int_corpus(rng, nq, d)
+    D, I, st = build(fa, xb).search_ex(xq, k, path=AUTO)
+    assert st["n_fast"] + st["n_exact"] == nq
+    assert_topk_parity(D, I, xb, xq, k, exact=True, what=f"auto path {st}")
+    Do, Io = oracle.flat_ip_search(xb, xq, k)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(100000, 128, 16, 10), (50000, 1024, 8, 20), (200000, 64, 64, 100),
+                                      (60000, 1024, 256, 20), (30000, 768, 1, 10)])
+def test_auto_path_unit_vectors_uses_the_filter(fa, n, d, nq, k):
+    rng = np.random.default_rng(n + k)
+    xb, xq = unit_rows(rng, n, d), unit_rows(rng, nq, d)
+    ix = build(fa, xb)
+    D, I, st = ix.search_ex(xq, k, path=AUTO)
+    assert st["n_fast"] >= nq * 0.9, st  # i.i.d. data: the certificate passes
+    assert st["levels"] >= 2 and st["n_overflow"] == 0, st
+    n_swaps = assert_topk_parity(D, I, xb, xq, k, what=f"auto path {st}")
+    # the two paths return bit-identical scores (canonical summation order) and ids
+    De, Ie, _ = ix.search_ex(xq, k, path=EXACT)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De), f"fast vs exact differ (near-tie swaps vs fp64: {n_swaps})"
+
+
+def test_fast_path_without_escalation_reports_certificate(fa):
+    rng = np.random.default_rng(5)
+    xb, xq = unit_rows(rng, 50000, 128), unit_rows(rng, 12, 128)
+    D, I, st = build(fa, xb).search_ex(xq, 10, path=FAST)
+    assert st["n_exact"] == 0 and st["n_fast"] == 12
+    assert_topk_parity(D, I, xb, xq, 10, what="fast path")
+
+
+def test_duplicates_lower_id_wins(fa):
+    rng = np.random.default_rng(6)
+    xb = unit_rows(rng, 30000, 128)
+    src = rng.choice(30000, 300, replace=False)
+    dst = rng.choice(30000, 300, replace=False)
+    xb[dst] = xb[src]
+    xq = xb[src[:8]] + 0.05 * rng.standard_normal((8, 128)).astype(np.float32)
+    D, I, st = build(fa, xb).search_ex(xq, 10, path=AUTO)
+    assert_topk_parity(D, I, xb, xq, 10, what=f"duplicates {st}")
+    for r in range(8):
+        ids, sc = I[r].tolist(), D[r].tolist()
+        for a in range(9):
+            if sc[a] == sc[a + 1]:
+                assert ids[a] < ids[a + 1]
+
+
+def test_clustered_data_escalates_and_stays_exact(fa):
+    """Tight clusters: rank-k and rank-4k scores are closer than the bf16 error bound, so the
+    certificate must fail and the exact scan must answer — results stay exact."""
+    rng = np.random.default_rng(7)
+    centers = unit_rows(rng, 8, 128)
+    xb = centers[rng.integers(0, 8, 20000)] + 1e-4 * rng.standard_normal((20000, 128)).astype(np.float32)
+    xb = (xb / np.linalg.norm(xb, axis=1, keepdims=True)).astype(np.float32)
+    xq = centers[:4]
+    D, I, st = build(fa, xb).search_ex(xq, 10, path=AUTO)
+    assert st["n_exact"] >= 1, st
+    assert_topk_parity(D, I, xb, xq, 10, what=f"clustered {st}")
+
+
+def test_sorted_corpus_is_not_pathological(fa):
+    """Rows sorted by similarity to the query (best last): the permuted tile walk keeps levels representative."""
+    rng = np.random.default_rng(8)
+    xb, xq = unit_rows(rng, 100000, 64), unit_rows(rng, 1, 64)
+    order = np.argsort(xb @ xq[0])
+    xb = np.ascontiguousarray(xb[order])
+    D, I, st = build(fa, xb).search_ex(xq, 10, path=AUTO)
+    assert st["n_overflow"] == 0, st
+    assert_topk_parity(D, I, xb, xq, 10, what=f"sorted {st}")
+
+
+def test_all_equal_scores_overflow_falls_back(fa):
+    xb = np.ones((50000, 64), dtype=np.float32)
+    xq = np.ones((2, 64), dtype=np.float32)
+    D, I, st = build(fa, xb).search_ex(xq, 10, path=AUTO)
+    assert I.tolist() == [list(range(10))] * 2 and np.all(D == 64.0)
+    assert st["n_exact"] == 2, st
+
+
+def test_planted_neighbours(fa):
+    rng = np.random.default_rng(10)
+    xb = unit_rows(rng, 80000, 256)
+    tgt = rng.choice(80000, 20, replace=False)
+    xq = xb[tgt] + 0.3 * unit_rows(rng, 20, 256)
+    xq = (xq / np.linalg.norm(xq, axis=1, keepdims=True)).astype(np.float32)
+    D, I, st = build(fa, xb).search_ex(xq, 20, path=AUTO)
+    assert np.array_equal(I[:, 0], tgt)
+    assert_topk_parity(D, I, xb, xq, 20, what=f"planted {st}")
+
+
+# ----------------------------------------------------------- index plumbing ---
+def test_incremental_add_growth_and_reconstruct(fa):
+    rng = np.random.default_rng(11)
+    xb = int_corpus(rng, 5000, 64)
+    ix = fa.IndexFlatIP(64)
+    for a, b in ((0, 1), (1, 130), (130, 131), (131, 3000), (3000, 5000)):
+        ix.add(xb[a:b])
+    assert ix.ntotal == 5000
+    assert np.array_equal(ix.reconstruct_n(0, 5000), xb)
+    assert np.array_equal(ix.reconstruct(4321), xb[4321])
+    xq = int_corpus(rng, 6, 64)
+    D, I, _ = ix.search_ex(xq, 10, path=AUTO)
+    assert_topk_parity(D, I, xb, xq, 10, exact=True)
+
+
+def test_id_offset(fa):
+    rng = np.random.default_rng(12)
+    xb, xq = int_corpus(rng, 2000, 64), int_corpus(rng, 3, 64)
+    ix = build(fa, xb)
+    D0, I0, _ = ix.search_ex(xq, 2100, path=EXACT)
+    D1, I1, _ = ix.search_ex(xq, 2100, path=EXACT, id_offset=10**10)
+    assert np.array_equal(D0, D1)
+    assert np.array_equal(np.where(I0 >= 0, I0 + 10**10, -1), I1)
+
+
+def test_save_load_roundtrip_and_container_is_ixfi(fa, tmp_path):
+    rng = np.random.default_rng(13)
+    xb, xq = unit_rows(rng, 3000, 64), unit_rows(rng, 4, 64)
+    ix = build(fa, xb)
+    p = str(tmp_path / "index.faiss")
+    fa.write_index(ix, p)
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"IxFI" and len(raw) == 45 + xb.nbytes
+    ox = oracle._read_index(p)  # an independent reader of the same container
+    assert np.array_equal(ox.reconstruct_n(), xb)
+    ix2 = fa.read_index(p, fa.IO_FLAG_MMAP)
+    assert ix2.ntotal == 3000 and ix2.d == 64
+    D1, I1 = ix.search(xq, 10)
+    D2, I2 = ix2.search(xq, 10)
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+    # and the reverse: a file written by the independent writer loads here
+    p2 = str(tmp_path / "other.faiss")
+    oracle._write_index(ox, p2)
+    assert np.array_equal(fa.read_index(p2).reconstruct_n(), xb)
+    with pytest.raises(RuntimeError):
+        fa.read_index(str(tmp_path / "missing.faiss"))
+
+
+def test_search_golden_fixture(fa):
+    z = np.load(os.path.join(GOLD, "search_golden.npz"))
+    for name in ("unit_64", "unit_1024", "kgtn", "ties"):
+        xb, xq, k = z[f"{name}_xb"], z[f"{name}_xq"], int(z[f"{name}_k"])
+        ix = build(fa, xb)
+        for path in (AUTO, EXACT):
+            D, I, st = ix.search_ex(xq, k, path=path)
+            assert np.array_equal(I, z[f"{name}_I"]), (name, path, st)
+            np.testing.assert_allclose(D, z[f"{name}_D"], rtol=1e-5, atol=1e-6)
+            if name == "ties":
+                assert np.array_equal(D, z[f"{name}_D"])
+
+
+def test_aligner_scoring_matches_reference_torch_golden(fa):
+    from kirag_b200.scoring import filter_candidate_triples_scores
+
+    z = np.load(os.path.join(GOLD, "aligner_golden.npz"))
+    for name in ("s", "m", "few"):
+        q, t, k = z[f"{name}_q"], z[f"{name}_t"], int(z[f"{name}_k"])
+        idx, sc = filter_candidate_triples_scores(q, t, k)
+        ref_s, ref_i = z[f"{name}_scores"], z[f"{name}_indices"]
+        assert np.asarray(sc).shape == ref_s.shape
+        np.testing.assert_allclose(np.asarray(sc, dtype=np.float32), ref_s, rtol=1e-5, atol=1e-6)
+        for r in range(q.shape[0]):
+            assert set(idx[r]) == set(ref_i[r].tolist())
+
+
+def test_config4_aligner_shape(fa):
+    """BASELINE configs[4]: 256 chain queries x 50k candidate triples, top-20."""
+    rng = np.random.default_rng(14)
+    t, q = unit_rows(rng, 50000, 1024), unit_rows(rng, 256, 1024)
+    from kirag_b200.scoring import topk_inner_product
+
+    D, I = topk_inner_product(q, t, 20)
+    assert_topk_parity(D, I, t, q, 20, what="aligner 256x50k")
+
+
+def test_device_pointer_entry_points(fa):
+    import torch
+
+    rng = np.random.default_rng(15)
+    xb, xq = unit_rows(rng, 40000, 128), unit_rows(rng, 10, 128)
+    ix = fa.IndexFlatIP(128)
+    ix.add_device(torch.from_numpy(xb).cuda())
+    D, I = ix.search_device(torch.from_numpy(xq).cuda(), 10, id_offset=5)
+    torch.cuda.synchronize()
+    assert_topk_parity(D.cpu().numpy(), I.cpu().numpy() - 5, xb, xq, 10, what="device pointers")
