@@ -246,7 +246,8 @@ static bool fast_eligible(const kirag_index* h, int k, FastParams* fp) {
     cap = env_int("KIRAG_CAND_CAP", cap);
     if (cap > kSelectSeg) cap = kSelectSeg;
     if (cap < 4 * kp) return false;
-    int growth = (int)(cap / (2 * kp));
+    // expected survivors of a level = k' * growth (incl. the k' kept); keep 4x headroom in the buffer
+    int growth = (int)(cap / (4 * kp));
     if (growth > 16) growth = 16;
     if (growth < 2) growth = 2;
     growth = env_int("KIRAG_LEVEL_GROWTH", growth);
@@ -321,7 +322,10 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
                                 h->overflow.as<int>(), st)) return 1;
         ++levels;
         lo = hi;
-        int64_t nh = hi * fp.growth;
+        // the first levels see few distinct tiles, so their tau is a noisy estimate when rows are
+        // clustered by position: grow gently at first
+        const int g = (levels <= 2 && fp.growth > 4) ? 4 : fp.growth;
+        int64_t nh = hi * g;
         hi = (nh > n_tiles) ? n_tiles : nh;
     }
     if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), fp.cap, fp.kprime,
