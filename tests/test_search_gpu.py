@@ -239,8 +239,8 @@ def test_id_offset(fa):
     rng = np.random.default_rng(12)
     xb, xq = int_corpus(rng, 2000, 64), int_corpus(rng, 3, 64)
     ix = build(fa, xb)
-    D0, I0, _ = ix.search_ex(xq, 2100, path=EXACT)
-    D1, I1, _ = ix.search_ex(xq, 2100, path=EXACT, id_offset=10**10)
+    D0, I0, _ = ix.search_ex(xq, 2040, path=EXACT)
+    D1, I1, _ = ix.search_ex(xq, 2040, path=EXACT, id_offset=10**10)
     assert np.array_equal(D0, D1)
     assert np.array_equal(np.where(I0 >= 0, I0 + 10**10, -1), I1)
 
