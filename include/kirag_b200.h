@@ -89,6 +89,9 @@ int kirag_device_count(void);
  * then clears. */
 int kirag_profile_enable(int on);
 int kirag_profile_read(double* scan_ms, int64_t* scan_launches, double* scan_rows);
+/* Per-launch durations (ms) and corpus rows of the recorded scan launches, up to max_n entries;
+ * does not clear (call before kirag_profile_read). */
+int kirag_profile_read_launches(double* ms_out, double* rows_out, int64_t max_n);
 
 /* ---- flat inner-product index  (replaces faiss.IndexFlatIP) ------------ */
 

@@ -45,6 +45,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 struct ScanProfile {
     bool on = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    std::vector<double> launch_rows;
     double rows = 0.0;  // corpus rows streamed by the recorded launches
     double queries = 0.0;
 };
@@ -292,7 +293,7 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     KIRAG_CUDA_OK(cudaMemsetAsync(h->overflow.p, 0, (size_t)nq * 4, st));
     if (fill_f32(h->tau.as<float>(), INFINITY, nq_pad, st)) return 1;  // pad queries never pass
     if (fill_f32(h->tau.as<float>(), -INFINITY, nq, st)) return 1;
-    if (launch_convert_rows(qd, nq, d, 0, h->qshadow.p, plan.bq, nullptr, h->qnorm.as<float>(), st)) return 1;
+    if (launch_convert_rows(qd, nq, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, h->qnorm.as<float>(), st)) return 1;
 
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
     const int64_t mult = pick_tile_mult(n_tiles);
@@ -315,6 +316,7 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
             g_prof.ev.emplace_back(e0, e1);
             int64_t r1 = hi * kTileRows; if (r1 > n) r1 = n;
             g_prof.rows += (double)(r1 - lo * kTileRows);
+            g_prof.launch_rows.push_back((double)(r1 - lo * kTileRows));
             g_prof.queries = (double)nq;
         }
         if (launch_select_pairs(h->cand.as<Cand>(), fp.cap, h->cnt.as<int>(), 0, fp.cap, (int)nq, fp.kprime,
@@ -444,8 +446,24 @@ int kirag_device_count(void) {
 int kirag_profile_enable(int on) {
     for (auto& pr : g_prof.ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     g_prof.ev.clear();
+    g_prof.launch_rows.clear();
     g_prof.rows = 0.0;
     g_prof.on = on != 0;
+    return 0;
+}
+
+int kirag_profile_read_launches(double* ms_out, double* rows_out, int64_t max_n) {
+    // per-launch durations (does not clear; call before kirag_profile_read)
+    int64_t i = 0;
+    for (auto& pr : g_prof.ev) {
+        if (i >= max_n) break;
+        KIRAG_CUDA_OK(cudaEventSynchronize(pr.second));
+        float t = 0.f;
+        KIRAG_CUDA_OK(cudaEventElapsedTime(&t, pr.first, pr.second));
+        if (ms_out) ms_out[i] = t;
+        if (rows_out) rows_out[i] = g_prof.launch_rows[(size_t)i];
+        ++i;
+    }
     return 0;
 }
 
@@ -462,6 +480,7 @@ int kirag_profile_read(double* scan_ms, int64_t* scan_launches, double* scan_row
     if (scan_rows) *scan_rows = g_prof.rows;
     for (auto& pr : g_prof.ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     g_prof.ev.clear();
+    g_prof.launch_rows.clear();
     g_prof.rows = 0.0;
     return 0;
 }
@@ -590,7 +609,13 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
     ScanTcPlan plan;
     if (scan_tc_pick(nq, d, &plan)) return 1;
     const char* force = getenv("KIRAG_DEBUG_BQ");
-    if (force && *force) { plan.bq = atoi(force); plan.resident = (plan.bq == 32) ? 1 : 0; }
+    if (force && *force) {
+        plan.bq = atoi(force);
+        plan.pair = 0;
+        if (plan.bq == 512) { plan.bq = 256; plan.pair = 1; }  // KIRAG_DEBUG_BQ=512 selects the 2-CTA kernel
+        plan.resident = (plan.bq == 32) ? 1 : 0;
+        plan.q_tile_rows = plan.pair ? 128 : plan.bq;
+    }
     const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
     const int64_t nq_pad = round_up(nq, 256);
     DevBuf qd, qs, tau, cnt, dump;
@@ -603,7 +628,7 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
         if (cudaMemsetAsync(cnt.p, 0, (size_t)nq_pad * 4, st) != cudaSuccess) break;
         if (cudaMemsetAsync(dump.p, 0, (size_t)h->ntotal * nq * 4, st) != cudaSuccess) break;
         if (fill_f32(tau.as<float>(), INFINITY, nq_pad, st)) break;
-        if (launch_convert_rows(qd.as<float>(), nq, d, 0, qs.p, plan.bq, nullptr, nullptr, st)) break;
+        if (launch_convert_rows(qd.as<float>(), nq, d, 0, qs.p, plan.q_tile_rows, nullptr, nullptr, st)) break;
         if (launch_scan_tc_dump(h->shadow, h->ntotal, d, qs.p, nq, plan, tau.as<float>(), cnt.as<int>(),
                                 dump.as<float>(), nq, h->num_sms, st)) break;
         if (cudaMemcpyAsync(out_host, dump.p, (size_t)h->ntotal * nq * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||

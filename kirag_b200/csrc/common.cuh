@@ -176,8 +176,10 @@ int launch_merge(const float* D_all, const int64_t* I_all, int G, int64_t nq, in
 int launch_fill_pad(float* D, int64_t* I, int64_t n, cudaStream_t st);
 // scan_tc.cu
 struct ScanTcPlan {
-    int bq;        // query-tile width (UMMA N)
-    int resident;  // 1: query tile stays in shared memory for the whole launch
+    int bq;           // query-tile width (UMMA N)
+    int resident;     // 1: query tile stays in shared memory for the whole launch
+    int pair;         // 1: 2-CTA (cta_group::2) kernel, M = 256 corpus rows per MMA
+    int q_tile_rows;  // rows per tile of the query shadow layout (bq, or bq/2 for the pair kernel)
 };
 int scan_tc_supported(int d);
 int scan_tc_pick(int64_t nq, int d, ScanTcPlan* plan);

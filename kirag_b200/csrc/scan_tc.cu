@@ -27,6 +27,7 @@
 // flops per launch).
 #include "common.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace kirag {
 
@@ -121,6 +122,53 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- 2-CTA (cta_group::2) variants -------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a local shared-memory object) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope): a cluster-scope release costs a ~1k-cycle fence per
+    // arrive, which serialised the forwarder; the data being signalled was written by the async
+    // proxy and its arrival is already ordered by the local mbarrier that was waited on
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* holder_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -132,6 +180,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    return r;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -168,9 +221,161 @@ struct ScanArgs {
     int64_t dump_ld;
 };
 
+// ---------------------------------------------------------------- filter ----
+// One thread = one corpus row; a warp owns NG groups of 32 query columns of the accumulator.
+// Pass 1 reads every group from TMEM and keeps only a 32-bit "score >= tau[q]" mask per group.
+// If nothing passed (the common case after the first levels) the accumulator is released at once.
+// Otherwise lane c plays "owner of query column c" in every group: one ballot per column, then the
+// counters of ALL groups are bumped by NG independent atomic instructions (one round trip in
+// total, not one per group), and pass 2 re-reads from TMEM only the groups that have survivors
+// and stores (score, row) at the reserved slots.
+__device__ __forceinline__ uint32_t pass_mask(const ScanArgs& a, const uint32_t (&v)[32], int64_t q0, int64_t row,
+                                              bool row_ok) {
+    const float4* tp = reinterpret_cast<const float4*>(a.tau + q0);
+    uint32_t pass = 0;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 t = __ldg(tp + c4);
+        pass |= (__uint_as_float(v[c4 * 4 + 0]) >= t.x ? 1u : 0u) << (c4 * 4 + 0);
+        pass |= (__uint_as_float(v[c4 * 4 + 1]) >= t.y ? 1u : 0u) << (c4 * 4 + 1);
+        pass |= (__uint_as_float(v[c4 * 4 + 2]) >= t.z ? 1u : 0u) << (c4 * 4 + 2);
+        pass |= (__uint_as_float(v[c4 * 4 + 3]) >= t.w ? 1u : 0u) << (c4 * 4 + 3);
+    }
+    if (!row_ok) pass = 0;
+    if (a.dump && row_ok) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (q0 + c < a.nq) a.dump[row * a.dump_ld + q0 + c] = __uint_as_float(v[c]);
+    }
+    return pass;
+}
+
+// After the first levels survivors are rare (a row beats tau[q] for ~k'*growth of millions of rows),
+// so a thread almost never has more than a few per work item: they are parked in a 4-entry
+// per-thread register list (Stash).  The accumulator is released right after the last TMEM read;
+// the slots are then reserved with independent atomics (all entries, all lanes, in flight
+// together) and the (score, row) pairs are stored one work item LATER, after the next item's TMEM
+// pass — the atomic round trip is never exposed to the tensor pipe.  A group in which some thread
+// would overflow its list (the dense first levels) is appended immediately instead.
+constexpr int kStash = 4;
+struct Stash {
+    uint32_t sv[kStash];  // score bits
+    int sc[kStash];       // query column inside this warp's column range
+    int slot[kStash];     // reserved buffer slot (valid after stash_reserve)
+    int n;
+    int64_t q0;
+    int32_t row;
+};
+__device__ __forceinline__ void stash_clear(Stash& st) {
+    st.n = 0;
+    st.q0 = 0;
+    st.row = 0;
+#pragma unroll
+    for (int j = 0; j < kStash; ++j) { st.sv[j] = 0; st.sc[j] = 0; st.slot[j] = -1; }
+}
+__device__ __forceinline__ void stash_reserve(const ScanArgs& a, Stash& st) {
+#pragma unroll
+    for (int j = 0; j < kStash; ++j) {
+        st.slot[j] = -1;
+        if (st.n > j && st.q0 + st.sc[j] < a.nq) st.slot[j] = atomicAdd(a.cnt + st.q0 + st.sc[j], 1);
+    }
+}
+__device__ __forceinline__ void stash_store(const ScanArgs& a, const Stash& st) {
+#pragma unroll
+    for (int j = 0; j < kStash; ++j) {
+        if (st.n > j && st.slot[j] >= 0 && st.slot[j] < a.cap) {
+            Cand cd;
+            cd.s = __uint_as_float(st.sv[j]);
+            cd.id = st.row;
+            a.cand[(st.q0 + st.sc[j]) * (int64_t)a.cap + st.slot[j]] = cd;
+        }
+    }
+}
+
+// Survivors of one 32-column group.  Deliberately compact, rolled code (it is replicated nowhere and
+// stays out of the instruction cache's way): the surviving columns are re-read one at a time from
+// TMEM (tcgen05.ld x1, dynamic column address) instead of indexing the 32 score registers.
+//   sparse (normal) : every thread parks its few survivors in its Stash
+//   dense (first levels, or a thread would overflow its Stash): lane c owns query column c, one
+//           ballot per surviving column, ONE atomic instruction bumps all counters, then the
+//           columns are stored at the reserved slots
+__device__ __forceinline__ void handle_survivors(const ScanArgs& a, uint32_t taddr_g, uint32_t pass, int64_t q0g,
+                                              int col_g, int32_t row, int lane, Stash& st) {
+    const unsigned uni = __reduce_or_sync(0xffffffffu, pass);
+    const bool dense = __any_sync(0xffffffffu, st.n + __popc(pass) > kStash);
+    if (!dense) {
+        for (unsigned u = uni; u; u &= u - 1) {
+            const int c = __ffs(u) - 1;
+            const uint32_t val = tmem_ld1(taddr_g + c);
+            tmem_ld_wait();
+            if ((pass >> c) & 1u) {
+#pragma unroll
+                for (int j = 0; j < kStash; ++j)
+                    if (st.n == j) { st.sv[j] = val; st.sc[j] = col_g + c; }
+                ++st.n;
+            }
+        }
+        return;
+    }
+    unsigned mybal = 0;
+    for (unsigned u = uni; u; u &= u - 1) {
+        const int c = __ffs(u) - 1;
+        const unsigned bal = __ballot_sync(0xffffffffu, (pass >> c) & 1u);
+        if (lane == c) mybal = bal;
+    }
+    if (q0g + lane >= a.nq) mybal = 0;
+    int mybase = 0;
+    if (mybal != 0) mybase = atomicAdd(a.cnt + q0g + lane, __popc(mybal));
+    const unsigned lt = (1u << lane) - 1u;
+    for (unsigned u = uni; u; u &= u - 1) {
+        const int c = __ffs(u) - 1;
+        const unsigned bal = __shfl_sync(0xffffffffu, mybal, c);
+        const int base = __shfl_sync(0xffffffffu, mybase, c);
+        const uint32_t val = tmem_ld1(taddr_g + c);
+        tmem_ld_wait();
+        if ((bal >> lane) & 1u) {
+            const int slot = base + __popc(bal & lt);
+            if (slot < a.cap) {
+                Cand cd;
+                cd.s = __uint_as_float(val);
+                cd.id = row;
+                a.cand[(q0g + c) * (int64_t)a.cap + slot] = cd;
+            }
+        }
+    }
+}
+
+// taddr: TMEM address of this warp's first column (lane quadrant included); q0: first query of it.
+// `release` is called exactly once, right after this warp's last read of the accumulator.
+template <int NG, typename Release>
+__device__ __forceinline__ void filter_item(const ScanArgs& a, uint32_t taddr, int64_t q0, int64_t row, bool row_ok,
+                                            int lane, Stash& st, Release release) {
+    stash_clear(st);
+    st.q0 = q0;
+    st.row = (int32_t)row;
+#pragma unroll 1
+    for (int g = 0; g < NG; ++g) {
+        uint32_t v[32];
+        tmem_ld32(taddr + g * 32, v);
+        tmem_ld_wait();
+        const uint32_t pass = pass_mask(a, v, q0 + g * 32, row, row_ok);
+        if (__any_sync(0xffffffffu, pass != 0))
+            handle_survivors(a, taddr + g * 32, pass, q0 + g * 32, g * 32, (int32_t)row, lane, st);
+    }
+    release();
+}
+
 // ---------------------------------------------------------------- kernel ----
+// filter warps: 4 (one per TMEM lane quadrant), or 8 for wide query tiles (two warps per quadrant,
+// each taking half of the columns)
+template <int BQ> struct EpiCfg {
+    static constexpr int kWarps = (BQ >= 128) ? 8 : 4;
+    static constexpr int kThreads = 64 + 32 * kWarps;
+    static constexpr int kGroups = BQ / 32 / (kWarps / 4);  // 32-column groups per warp
+};
+
 template <int BQ, bool RESIDENT>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_tc_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const ScanArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -192,10 +397,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tc_kernel(const ScanArgs
     const int lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = (2 * BQ <= 32) ? 32 : (2 * BQ <= 64) ? 64 : (2 * BQ <= 128) ? 128 : (2 * BQ <= 256) ? 256 : 512;
     const int n_qt = (int)((a.nq + BQ - 1) / BQ);
+    // work item w = (walk position, query tile), query tile fastest so that a CTA re-reads its corpus
+    // tile from L2; every CTA takes one contiguous, equally sized range of w
+    const int64_t W = (a.tile_hi - a.tile_lo) * n_qt;
+    const int64_t w_lo = W * blockIdx.x / gridDim.x;
+    const int64_t w_hi = W * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EpiCfg<BQ>::kWarps); }
         mbar_init(q_bar, 1);
         fence_barrier_init();
     }
@@ -216,20 +426,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tc_kernel(const ScanArgs
             }
             int s = 0;
             uint32_t ph = 0;
-            for (int64_t ti = a.tile_lo + blockIdx.x; ti < a.tile_hi; ti += gridDim.x) {
-                const int64_t tile = (ti * a.tile_mult) % a.n_tiles;
+            for (int64_t w = w_lo; w < w_hi; ++w) {
+                const int64_t tp = w / n_qt;
+                const int qt = (int)(w - tp * n_qt);
+                const int64_t tile = ((a.tile_lo + tp) * a.tile_mult) % a.n_tiles;
                 const uint8_t* xsrc = a.shadow + (size_t)tile * ((size_t)a.d * kTileRows * 2);
-                for (int qt = 0; qt < n_qt; ++qt) {
-                    const uint8_t* qsrc = a.qshadow + (size_t)qt * ((size_t)a.d * BQ * 2);
-                    for (int kc = 0; kc < KC; ++kc) {
-                        mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
-                        uint8_t* dst = stage_base + (size_t)s * stage_bytes;
-                        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                        bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
-                        if (!RESIDENT)
-                            bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQBlockBytes, kQBlockBytes, &full_bar[s], pol_q);
-                        if (++s == NS) { s = 0; ph ^= 1u; }
-                    }
+                const uint8_t* qsrc = a.qshadow + (size_t)qt * ((size_t)a.d * BQ * 2);
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
+                    uint8_t* dst = stage_base + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                    bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
+                    if (!RESIDENT)
+                        bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQBlockBytes, kQBlockBytes, &full_bar[s], pol_q);
+                    if (++s == NS) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -241,106 +451,239 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_tc_kernel(const ScanArgs
             int s = 0;
             uint32_t ph = 0;
             uint32_t it = 0;
-            for (int64_t ti = a.tile_lo + blockIdx.x; ti < a.tile_hi; ti += gridDim.x) {
-                for (int qt = 0; qt < n_qt; ++qt, ++it) {
-                    const uint32_t as = it & 1u;
-                    const uint32_t aph = (it >> 1) & 1u;
-                    mbar_wait(&tmem_empty[as], aph ^ 1u, 300 + as);
+            for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
+                const uint32_t as = it & 1u;
+                const uint32_t aph = (it >> 1) & 1u;
+                mbar_wait(&tmem_empty[as], aph ^ 1u, 300 + as);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BQ;
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&full_bar[s], ph, 400 + s);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + as * BQ;
-                    for (int kc = 0; kc < KC; ++kc) {
-                        mbar_wait(&full_bar[s], ph, 400 + s);
-                        tc_fence_after();
-                        const uint32_t xa = smem_u32(stage_base + (size_t)s * stage_bytes);
-                        const uint32_t qa = RESIDENT ? smem_u32(q_res + (size_t)kc * kQBlockBytes) : xa + kBlockBytes;
-                        const uint64_t da = make_sw128_desc(xa);
-                        const uint64_t db = make_sw128_desc(qa);
+                    const uint32_t xa = smem_u32(stage_base + (size_t)s * stage_bytes);
+                    const uint32_t qa = RESIDENT ? smem_u32(q_res + (size_t)kc * kQBlockBytes) : xa + kBlockBytes;
+                    const uint64_t da = make_sw128_desc(xa);
+                    const uint64_t db = make_sw128_desc(qa);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            // +32 bytes (two 16-byte units) per K=16 step inside the 128-byte swizzle row
-                            umma_bf16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
-                                      (kc | k4) ? 1u : 0u);
-                        }
-                        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
-                        if (++s == NS) { s = 0; ph ^= 1u; }
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        // +32 bytes (two 16-byte units) per K=16 step inside the 128-byte swizzle row
+                        umma_bf16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
+                                  (kc | k4) ? 1u : 0u);
                     }
-                    umma_commit(&tmem_full[as]);  // accumulator complete
+                    umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+                    if (++s == NS) { s = 0; ph ^= 1u; }
                 }
+                umma_commit(&tmem_full[as]);  // accumulator complete
             }
         }
     } else {
         // ================================ filter ================================
         const int quad = warp & 3;  // TMEM lane quadrant this warp may read
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        constexpr int NG = EpiCfg<BQ>::kGroups;
+        const int col0 = ((warp - 2) >> 2) * (NG * 32);  // this warp's first column inside the query tile
         uint32_t it = 0;
-        for (int64_t ti = a.tile_lo + blockIdx.x; ti < a.tile_hi; ti += gridDim.x) {
-            const int64_t tile = (ti * a.tile_mult) % a.n_tiles;
+        Stash pend, cur;
+        stash_clear(pend);
+        for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
+            const int64_t tp = w / n_qt;
+            const int qt = (int)(w - tp * n_qt);
+            const int64_t tile = ((a.tile_lo + tp) * a.tile_mult) % a.n_tiles;
             const int64_t row = tile * kTileRows + quad * 32 + lane;
             const bool row_ok = row < a.n_rows;
-            for (int qt = 0; qt < n_qt; ++qt, ++it) {
-                const uint32_t as = it & 1u;
-                const uint32_t aph = (it >> 1) & 1u;
-                mbar_wait(&tmem_full[as], aph, 500 + as);
-                tc_fence_after();
-#pragma unroll 1
-                for (int g = 0; g < BQ / 32; ++g) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + as * BQ + g * 32, v);
-                    tmem_ld_wait();
-                    if (g == BQ / 32 - 1) {
-                        // all of this warp's reads of the accumulator are done
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[as]);
-                    }
-                    const int64_t q0 = (int64_t)qt * BQ + g * 32;
-                    const float4* tp = reinterpret_cast<const float4*>(a.tau + q0);
-                    uint32_t pass = 0;
-#pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 t = __ldg(tp + c4);
-                        pass |= (__uint_as_float(v[c4 * 4 + 0]) >= t.x ? 1u : 0u) << (c4 * 4 + 0);
-                        pass |= (__uint_as_float(v[c4 * 4 + 1]) >= t.y ? 1u : 0u) << (c4 * 4 + 1);
-                        pass |= (__uint_as_float(v[c4 * 4 + 2]) >= t.z ? 1u : 0u) << (c4 * 4 + 2);
-                        pass |= (__uint_as_float(v[c4 * 4 + 3]) >= t.w ? 1u : 0u) << (c4 * 4 + 3);
-                    }
-                    if (!row_ok) pass = 0;
-                    if (a.dump && row_ok) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (q0 + c < a.nq) a.dump[row * a.dump_ld + q0 + c] = __uint_as_float(v[c]);
-                    }
-                    if (__any_sync(0xffffffffu, pass != 0)) {
-                        // rare after the first level: warp-aggregated append, one atomic per (warp, query)
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const unsigned bal = __ballot_sync(0xffffffffu, (pass >> c) & 1u);
-                            if (bal != 0 && q0 + c < a.nq) {
-                                const int leader = __ffs(bal) - 1;
-                                int base = 0;
-                                if (lane == leader) base = atomicAdd(a.cnt + q0 + c, __popc(bal));
-                                base = __shfl_sync(0xffffffffu, base, leader);
-                                if ((pass >> c) & 1u) {
-                                    const int slot = base + __popc(bal & ((1u << lane) - 1u));
-                                    if (slot < a.cap) {
-                                        Cand cd;
-                                        cd.s = __uint_as_float(v[c]);
-                                        cd.id = (int32_t)row;
-                                        a.cand[(q0 + c) * (int64_t)a.cap + slot] = cd;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+            const uint32_t as = it & 1u;
+            const uint32_t aph = (it >> 1) & 1u;
+            mbar_wait(&tmem_full[as], aph, 500 + as);
+            tc_fence_after();
+            uint64_t* const ebar = &tmem_empty[as];
+            filter_item<NG>(a, tmem_base + lane_base + as * BQ + col0, (int64_t)qt * BQ + col0, row, row_ok, lane,
+                            cur, [=]() {
+                                // all of this warp's reads of the accumulator are done
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(ebar);
+                            });
+            stash_store(a, pend);    // slots reserved one item ago
+            stash_reserve(a, cur);   // atomics in flight until the next item has been read
+            pend = cur;
         }
+        stash_store(a, pend);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------- 2-CTA pair kernel ----
+// Large query batches are tensor-bound, and with one CTA per tile the query operand makes
+// the L2 -> shared-memory traffic the limiter (48 KB per 128x256x64 MMA block).  Here two
+// CTAs on the two SMs of a TPC form a cluster and issue ONE tcgen05.mma.cta_group::2 of
+// M=256 (2 corpus tiles) x N=256 (queries) x K=16: each CTA stages only its own 16 KB corpus
+// block and HALF of the query block (16 KB), i.e. 32 KB per CTA for the same flops.
+//   rank 0 (leader): producer, MMA issuer, filter warps
+//   rank 1 (peer)  : producer, forwarder (tells the leader that the peer's stage is full),
+//                    filter warps
+// Barriers: full[s] lives in each CTA (leader: own expect_tx + the peer's forwarded arrive);
+// empty[s] and tmem_full[a] are signalled in both CTAs by a multicast tcgen05.commit;
+// tmem_empty[a] of the LEADER collects the 8 filter warps of both CTAs.
+constexpr int kPairQ = 256;       // queries per work item (UMMA N)
+constexpr int kPairHalfQ = 128;   // query rows staged per CTA
+constexpr int kPairStageBytes = kBlockBytes + kPairHalfQ * 128;  // 32 KB
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<kPairQ>::kThreads, 1)
+scan_tc_pair_kernel(const ScanArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int KC = a.d >> 6;
+    const int NS = a.n_stages;
+    uint8_t* stage_base = smem;
+    uint8_t* tail = smem + (size_t)NS * kPairStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int64_t pair = blockIdx.x >> 1;
+    const int64_t n_pairs = gridDim.x >> 1;
+    constexpr uint32_t kTmemCols = 512;
+    const int n_qt = (int)((a.nq + kPairQ - 1) / kPairQ);
+    // work item w = (pair of walk positions, 256-query tile), query tile fastest; every cluster takes
+    // one contiguous, equally sized range of w, so small levels still occupy all SM pairs
+    const int64_t W = ((a.tile_hi - a.tile_lo + 1) / 2) * n_qt;
+    const int64_t w_lo = W * pair / n_pairs;
+    const int64_t w_hi = W * (pair + 1) / n_pairs;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full_bar[s], rank == 0 ? 2 : 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EpiCfg<kPairQ>::kWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(tmem_holder, kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // tiles of this level are taken two at a time: walk position 2*p + rank
+    if (warp == 0) {
+        // =============================== producer ===============================
+        if (lane == 0) {
+            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : policy_evict_normal();
+            const uint64_t pol_q = policy_evict_last();
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t w = w_lo; w < w_hi; ++w) {
+                const int64_t p = w / n_qt;
+                const int qt = (int)(w - p * n_qt);
+                int64_t ti = a.tile_lo + 2 * p + rank;
+                if (ti >= a.tile_hi) ti = a.tile_hi - 1;  // odd tail: stage a valid tile, rows are masked later
+                const int64_t tile = (ti * a.tile_mult) % a.n_tiles;
+                const uint8_t* xsrc = a.shadow + (size_t)tile * ((size_t)a.d * kTileRows * 2);
+                // query shadow is stored in 128-row tiles: this CTA stages tile 2*qt + rank
+                const uint8_t* qsrc = a.qshadow + (size_t)(2 * qt + rank) * ((size_t)a.d * kPairHalfQ * 2);
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
+                    uint8_t* dst = stage_base + (size_t)s * kPairStageBytes;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)kPairStageBytes);
+                    bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
+                    bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * (kPairHalfQ * 128), kPairHalfQ * 128,
+                             &full_bar[s], pol_q);
+                    if (++s == NS) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            if (rank == 1) {
+                // ============================= forwarder =============================
+                for (int64_t w = w_lo; w < w_hi; ++w) {
+                    for (int kc = 0; kc < KC; ++kc) {
+                        mbar_wait(&full_bar[s], ph, 600 + s);               // this CTA's stage has landed
+                        mbar_arrive_cluster(map_to_rank(&full_bar[s], 0));  // tell the leader
+                        if (++s == NS) { s = 0; ph ^= 1u; }
+                    }
+                }
+            } else {
+                // ================================ MMA ================================
+                constexpr uint32_t idesc = make_idesc_bf16(2 * kTileRows, kPairQ);
+                uint32_t it = 0;
+                for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
+                    const uint32_t as = it & 1u;
+                    const uint32_t aph = (it >> 1) & 1u;
+                    mbar_wait(&tmem_empty[as], aph ^ 1u, 300 + as);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * kPairQ;
+                    for (int kc = 0; kc < KC; ++kc) {
+                        mbar_wait(&full_bar[s], ph, 400 + s);  // own bytes + the peer's forward
+                        tc_fence_after();
+                        const uint32_t xa = smem_u32(stage_base + (size_t)s * kPairStageBytes);
+                        const uint64_t da = make_sw128_desc(xa);
+                        const uint64_t db = make_sw128_desc(xa + kBlockBytes);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            umma_bf16_2cta(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
+                                           (kc | k4) ? 1u : 0u);
+                        umma_commit_2cta(&empty_bar[s]);
+                        if (++s == NS) { s = 0; ph ^= 1u; }
+                    }
+                    umma_commit_2cta(&tmem_full[as]);
+                }
+            }
+        }
+    } else {
+        // ================================ filter ================================
+        const int quad = warp & 3;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        uint32_t leader_empty[2];
+        leader_empty[0] = map_to_rank(&tmem_empty[0], 0);
+        leader_empty[1] = map_to_rank(&tmem_empty[1], 0);
+        constexpr int NG = EpiCfg<kPairQ>::kGroups;
+        const int col0 = ((warp - 2) >> 2) * (NG * 32);
+        uint32_t it = 0;
+        Stash pend, cur;
+        stash_clear(pend);
+        for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
+            const int64_t p = w / n_qt;
+            const int qt = (int)(w - p * n_qt);
+            const int64_t ti = a.tile_lo + 2 * p + rank;
+            const bool tile_ok = ti < a.tile_hi;
+            const int64_t tile = ((tile_ok ? ti : a.tile_hi - 1) * a.tile_mult) % a.n_tiles;
+            const int64_t row = tile * kTileRows + quad * 32 + lane;
+            const bool row_ok = tile_ok && row < a.n_rows;
+            const uint32_t as = it & 1u;
+            const uint32_t aph = (it >> 1) & 1u;
+            mbar_wait(&tmem_full[as], aph, 500 + as);
+            tc_fence_after();
+            const uint32_t ebar = leader_empty[as];
+            filter_item<NG>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
+                            lane, cur, [=]() {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(ebar);
+                            });
+            stash_store(a, pend);
+            stash_reserve(a, cur);
+            pend = cur;
+        }
+        stash_store(a, pend);
+    }
+    tc_fence_before();
+    cluster_sync_all();  // nobody leaves (or frees TMEM) while the partner can still signal into this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, kTmemCols);
     }
 }
 
@@ -361,18 +704,42 @@ static int pick_stages(int bq, bool resident, int d) {
     return ns;
 }
 
+static int env_flag(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 int scan_tc_pick(int64_t nq, int d, ScanTcPlan* plan) {
     KIRAG_CHECK(scan_tc_supported(d), "scan_tc: dimension %d is not supported (need a multiple of 64, <= 4096)", d);
+    plan->pair = 0;
     if (nq <= 32 && pick_stages(32, true, d) >= 4) { plan->bq = 32; plan->resident = 1; }
     else if (nq <= 64) { plan->bq = 64; plan->resident = 0; }
     else if (nq <= 128) { plan->bq = 128; plan->resident = 0; }
-    else { plan->bq = 256; plan->resident = 0; }
+    else { plan->bq = 256; plan->resident = 0; plan->pair = env_flag("KIRAG_SCAN_PAIR", 1) ? 1 : 0; }
+    plan->q_tile_rows = plan->pair ? kPairHalfQ : plan->bq;
     return 0;
 }
 
 size_t scan_tc_qshadow_bytes(int64_t nq, int d, const ScanTcPlan& plan) {
     const int64_t tiles = (nq + plan.bq - 1) / plan.bq;
     return (size_t)tiles * plan.bq * d * 2;
+}
+
+static int launch_scan_pair(const ScanArgs& args_in, int num_sms, cudaStream_t st) {
+    ScanArgs args = args_in;
+    int ns = kMaxStages;
+    const size_t fixed = 1024 + (2 * kMaxStages + 4) * 8 + 16;
+    while (ns > 0 && fixed + (size_t)ns * kPairStageBytes > (size_t)kSmemLimit) --ns;
+    KIRAG_CHECK(ns >= 2, "scan_tc pair: no room for a shared-memory pipeline");
+    args.n_stages = ns;
+    const size_t smem = fixed + (size_t)ns * kPairStageBytes;
+    KIRAG_CUDA_OK(cudaFuncSetAttribute(scan_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    int64_t pairs = ((args.tile_hi - args.tile_lo + 1) / 2) * ((args.nq + kPairQ - 1) / kPairQ);  // work items
+    if (pairs > num_sms / 2) pairs = num_sms / 2;
+    if (pairs <= 0) return 0;
+    scan_tc_pair_kernel<<<(unsigned)(2 * pairs), EpiCfg<kPairQ>::kThreads, smem, st>>>(args);
+    KIRAG_LAUNCH_OK("scan_tc_pair_kernel");
+    return 0;
 }
 
 template <int BQ, bool RESIDENT>
@@ -383,15 +750,17 @@ static int launch_scan_t(const ScanArgs& args_in, int num_sms, cudaStream_t st) 
     const size_t smem = scan_smem_bytes(BQ, RESIDENT, args.d, args.n_stages);
     KIRAG_CUDA_OK(cudaFuncSetAttribute(scan_tc_kernel<BQ, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemLimit));
-    int64_t grid = args.tile_hi - args.tile_lo;
+    const int64_t n_qt = (args.nq + BQ - 1) / BQ;
+    int64_t grid = (args.tile_hi - args.tile_lo) * n_qt;  // work items
     if (grid > num_sms) grid = num_sms;
     if (grid <= 0) return 0;
-    scan_tc_kernel<BQ, RESIDENT><<<(unsigned)grid, kScanThreads, smem, st>>>(args);
+    scan_tc_kernel<BQ, RESIDENT><<<(unsigned)grid, EpiCfg<BQ>::kThreads, smem, st>>>(args);
     KIRAG_LAUNCH_OK("scan_tc_kernel");
     return 0;
 }
 
 static int launch_scan_args(const ScanArgs& args, const ScanTcPlan& plan, int num_sms, cudaStream_t st) {
+    if (plan.pair) return launch_scan_pair(args, num_sms, st);
     if (plan.bq == 32 && plan.resident) return launch_scan_t<32, true>(args, num_sms, st);
     if (plan.bq == 64 && !plan.resident) return launch_scan_t<64, false>(args, num_sms, st);
     if (plan.bq == 128 && !plan.resident) return launch_scan_t<128, false>(args, num_sms, st);

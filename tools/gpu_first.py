@@ -43,6 +43,18 @@ for (n,d,nq) in ((300,64,40),(1000,128,100),(2000,1024,200),(1000,256,600)):
     bad=np.argwhere(got!=ref)
     print('tc streamed', (n,d,nq), 'exact' if len(bad)==0 else f'MISMATCH {len(bad)} of {got.size}; first {bad[:5].tolist()} got {got[tuple(bad[0])]} ref {ref[tuple(bad[0])]}' )
 """,
+    "tc_scores_pair": """
+import os, numpy as np
+os.environ['KIRAG_DEBUG_BQ']='512'
+from kirag_b200 import faiss_api
+rng=np.random.default_rng(0)
+for (n,d,nq) in ((256,64,256),(300,64,40),(1000,128,300),(2100,1024,520),(128,64,256),(129,256,1)):
+    xb=rng.integers(-3,4,size=(n,d)).astype(np.float32); xq=rng.integers(-3,4,size=(nq,d)).astype(np.float32)
+    ix=faiss_api.IndexFlatIP(d); ix.add(xb)
+    got=ix.debug_scores(xq); ref=(xb.astype(np.float64)@xq.astype(np.float64).T).astype(np.float32)
+    bad=np.argwhere(got!=ref)
+    print('tc pair', (n,d,nq), 'exact' if len(bad)==0 else f'MISMATCH {len(bad)} of {got.size}; first {bad[:5].tolist()} got {got[tuple(bad[0])]} ref {ref[tuple(bad[0])]}' )
+""",
     "auto_small": """
 import numpy as np
 from kirag_b200 import faiss_api
