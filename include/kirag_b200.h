@@ -92,6 +92,10 @@ int kirag_profile_read(double* scan_ms, int64_t* scan_launches, double* scan_row
 /* Per-launch durations (ms) and corpus rows of the recorded scan launches, up to max_n entries;
  * does not clear (call before kirag_profile_read). */
 int kirag_profile_read_launches(double* ms_out, double* rows_out, int64_t max_n);
+/* Timeline of the recorded search phases: tag 0 start, 1 queries converted, 10+l scan of level l
+ * done, 30+l select of level l done, 50 rescored, 51 final written; ms relative to the first mark.
+ * Returns the number of entries written; does not clear. */
+int kirag_profile_read_timeline(int* tags_out, double* ms_since_first, int64_t max_n);
 
 /* ---- flat inner-product index  (replaces faiss.IndexFlatIP) ------------ */
 

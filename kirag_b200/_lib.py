@@ -53,6 +53,7 @@ SIGNATURES = {
     "kirag_profile_enable": (c_int, [c_int]),
     "kirag_profile_read": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double)]),
     "kirag_profile_read_launches": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), c_int64]),
+    "kirag_profile_read_timeline": (c_int, [POINTER(c_int), POINTER(ctypes.c_double), c_int64]),
     "kirag_index_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
     "kirag_index_destroy": (c_int, [c_void_p]),
     "kirag_index_reserve": (c_int, [c_void_p, c_int64]),

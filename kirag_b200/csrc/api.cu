@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -39,6 +40,34 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+struct SmemAttrEntry { const void* kernel; int device; size_t bytes; };
+static std::vector<SmemAttrEntry> g_smem_attr;
+static std::mutex g_smem_attr_mu;
+int ensure_dynamic_smem_impl(const void* kernel, size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    std::lock_guard<std::mutex> lock(g_smem_attr_mu);
+    for (auto& e : g_smem_attr) {
+        if (e.kernel == kernel && e.device == dev) {
+            if (bytes <= e.bytes) return 0;
+            cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (err != cudaSuccess) {
+                set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", bytes, cudaGetErrorString(err));
+                return 1;
+            }
+            e.bytes = bytes;
+            return 0;
+        }
+    }
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", bytes, cudaGetErrorString(err));
+        return 1;
+    }
+    g_smem_attr.push_back({kernel, dev, bytes});
+    return 0;
+}
+
 // Optional per-kernel timing of the dominant kernel (the tcgen05 filter scan): CUDA events
 // recorded on the launching stream around every scan launch while enabled.  bench.py uses
 // it for the roofline line; it is off by default.
@@ -46,10 +75,21 @@ struct ScanProfile {
     bool on = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
     std::vector<double> launch_rows;
+    std::vector<std::pair<int, cudaEvent_t>> marks;  // (tag, event) timeline of the search phases
     double rows = 0.0;  // corpus rows streamed by the recorded launches
     double queries = 0.0;
 };
 static ScanProfile g_prof;
+
+// timeline tags: 0 start, 1 after convert/init, 10+l after scan of level l, 30+l after select of
+// level l, 50 after rescore, 51 after final, 52 after certificate readback
+static void prof_mark(int tag, cudaStream_t st) {
+    if (!g_prof.on) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof.marks.emplace_back(tag, e);
+}
 
 struct DevBuf {
     void* p = nullptr;
@@ -92,6 +132,13 @@ static int fill_f32(float* p, float v, int64_t n, cudaStream_t st) {
     fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, v, n);
     KIRAG_LAUNCH_OK("fill_f32_kernel");
     return 0;
+}
+
+// tau = -inf for real queries, +inf for the pad (pad queries never pass); counters and overflow flags zeroed
+__global__ void init_search_state_kernel(float* tau, int* cnt, int* overflow, int64_t nq, int64_t nq_pad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq_pad) tau[i] = (i < nq) ? -INFINITY : INFINITY;
+    if (i < nq) { cnt[i] = 0; overflow[i] = 0; }
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int d,
@@ -288,12 +335,14 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     if (h->overflow.ensure((size_t)nq * 4)) return 1;
     if (h->flags.ensure((size_t)nq * 4)) return 1;
     if (h->rescored.ensure((size_t)nq * fp.kprime * 4)) return 1;
-    KIRAG_CUDA_OK(cudaMemsetAsync(h->qshadow.p, 0, qs_bytes, st));
-    KIRAG_CUDA_OK(cudaMemsetAsync(h->cnt.p, 0, (size_t)nq * 4, st));
-    KIRAG_CUDA_OK(cudaMemsetAsync(h->overflow.p, 0, (size_t)nq * 4, st));
-    if (fill_f32(h->tau.as<float>(), INFINITY, nq_pad, st)) return 1;  // pad queries never pass
-    if (fill_f32(h->tau.as<float>(), -INFINITY, nq, st)) return 1;
+    if ((nq % plan.bq) != 0)  // only the pad rows of the last query tile need zeroing
+        KIRAG_CUDA_OK(cudaMemsetAsync(h->qshadow.p, 0, qs_bytes, st));
+    init_search_state_kernel<<<(unsigned)((nq_pad + 255) / 256), 256, 0, st>>>(h->tau.as<float>(), h->cnt.as<int>(),
+                                                                             h->overflow.as<int>(), nq, nq_pad);
+    KIRAG_LAUNCH_OK("init_search_state_kernel");
+    prof_mark(0, st);
     if (launch_convert_rows(qd, nq, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, h->qnorm.as<float>(), st)) return 1;
+    prof_mark(1, st);
 
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
     const int64_t mult = pick_tile_mult(n_tiles);
@@ -319,9 +368,10 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
             g_prof.launch_rows.push_back((double)(r1 - lo * kTileRows));
             g_prof.queries = (double)nq;
         }
-        if (launch_select_pairs(h->cand.as<Cand>(), fp.cap, h->cnt.as<int>(), 0, fp.cap, (int)nq, fp.kprime,
-                                h->cand.as<Cand>(), fp.cap, 1, h->tau.as<float>(), h->cnt.as<int>(),
-                                h->overflow.as<int>(), st)) return 1;
+        prof_mark(10 + levels, st);
+        if (launch_compact_topm(h->cand.as<Cand>(), fp.cap, h->cnt.as<int>(), fp.cap, (int)nq, fp.kprime,
+                                h->tau.as<float>(), h->overflow.as<int>(), st)) return 1;
+        prof_mark(30 + levels, st);
         ++levels;
         lo = hi;
         // the first levels see few distinct tiles, so their tau is a noisy estimate when rows are
@@ -332,12 +382,14 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     }
     if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), fp.cap, fp.kprime,
                        h->rescored.as<float>(), nq, st)) return 1;
+    prof_mark(50, st);
     // eps bounds |approx - canonical|: bf16 rounding of both operands (2 * 2^-9, plus
     // the cross term) and fp32 accumulation slack, times ||q|| * max_j ||x_j||
     const float eps_factor = (float)((ldexp(1.0, -8) * 1.002 + (double)d * ldexp(1.0, -21)) * (double)h->maxnorm);
     if (launch_final(h->cand.as<Cand>(), fp.cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, fp.kprime,
                      (int)nq, k, D, I, id_offset, h->tau.as<float>(), h->qnorm.as<float>(), eps_factor,
                      check_cert, h->overflow.as<int>(), h->flags.as<int>(), nullptr, st)) return 1;
+    prof_mark(51, st);
     if (levels_out) *levels_out = levels;
     return 0;
 }
@@ -447,9 +499,26 @@ int kirag_profile_enable(int on) {
     for (auto& pr : g_prof.ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     g_prof.ev.clear();
     g_prof.launch_rows.clear();
+    for (auto& mk : g_prof.marks) cudaEventDestroy(mk.second);
+    g_prof.marks.clear();
     g_prof.rows = 0.0;
     g_prof.on = on != 0;
     return 0;
+}
+
+int kirag_profile_read_timeline(int* tags_out, double* ms_since_first, int64_t max_n) {
+    // timeline of the recorded search phases (does not clear); ms are relative to the first mark
+    int64_t i = 0;
+    for (auto& mk : g_prof.marks) {
+        if (i >= max_n) break;
+        KIRAG_CUDA_OK(cudaEventSynchronize(mk.second));
+        float t = 0.f;
+        KIRAG_CUDA_OK(cudaEventElapsedTime(&t, g_prof.marks[0].second, mk.second));
+        if (tags_out) tags_out[i] = mk.first;
+        if (ms_since_first) ms_since_first[i] = t;
+        ++i;
+    }
+    return (int)i;
 }
 
 int kirag_profile_read_launches(double* ms_out, double* rows_out, int64_t max_n) {
@@ -481,6 +550,8 @@ int kirag_profile_read(double* scan_ms, int64_t* scan_launches, double* scan_row
     for (auto& pr : g_prof.ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     g_prof.ev.clear();
     g_prof.launch_rows.clear();
+    for (auto& mk : g_prof.marks) cudaEventDestroy(mk.second);
+    g_prof.marks.clear();
     g_prof.rows = 0.0;
     return 0;
 }

@@ -50,6 +50,15 @@ void count_launch(int n = 1);
         kirag::count_launch();                                                            \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a driver round trip; do it once per
+// (kernel, device) instead of before every launch.  Keyed by the kernel's address (different
+// template instantiations share one function-pointer TYPE).
+int ensure_dynamic_smem_impl(const void* kernel, size_t bytes);
+template <typename K>
+inline int ensure_dynamic_smem(K kernel, size_t bytes) {
+    return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 // ------------------------------------------------------- shadow geometry ---
 constexpr int kTileRows = 128;   // corpus rows per shadow tile (= UMMA M)
 constexpr int kKChunk = 64;      // bf16 elements per 128-byte swizzle row (= one k-block)
@@ -167,6 +176,8 @@ int launch_select_dense(const float* scores, int64_t ld, int64_t n, int nq, int 
 int launch_select_pairs(const Cand* in, int64_t in_stride, const int* cnt, int fixed_count, int cap,
                         int nq, int m, Cand* out, int64_t out_stride, int n_seg, float* tau,
                         int* cnt_out, int* overflow, cudaStream_t st);
+int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, int m, float* tau, int* overflow,
+                        cudaStream_t st);
 int launch_final(const Cand* cand, int64_t cand_stride, const float* rescored, const int* cnt,
                  int fixed_count, int m_in, int nq, int k, float* D, int64_t* I, int64_t id_offset,
                  const float* tau, const float* qnorm, float eps_factor, int check_cert,

@@ -298,15 +298,11 @@ static int pool_launch_t(const void* hidden, const void* mask, float* out, float
                      ((reinterpret_cast<uintptr_t>(hidden) % (esz * vec_elems)) == 0);
     const unsigned grid = (unsigned)(B * kPoolCluster);
     if (vec) {
-        if (smem > 48 * 1024)
-            KIRAG_CUDA_OK(cudaFuncSetAttribute(pool_normalize_kernel<T, true>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024 && ensure_dynamic_smem(pool_normalize_kernel<T, true>, smem)) return 1;
         pool_normalize_kernel<T, true><<<grid, kPoolThreads, smem, st>>>(
             (const T*)hidden, mask, out, pooled_norm, S, H, sb, ss, mb, mask_dtype, mode, normalize);
     } else {
-        if (smem > 48 * 1024)
-            KIRAG_CUDA_OK(cudaFuncSetAttribute(pool_normalize_kernel<T, false>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024 && ensure_dynamic_smem(pool_normalize_kernel<T, false>, smem)) return 1;
         pool_normalize_kernel<T, false><<<grid, kPoolThreads, smem, st>>>(
             (const T*)hidden, mask, out, pooled_norm, S, H, sb, ss, mb, mask_dtype, mode, normalize);
     }

@@ -90,15 +90,11 @@ int launch_scan_exact(const float* master, int64_t n, int d, const float* q, int
     if (blocks > max_blocks) blocks = max_blocks;
     const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(master) & 15) == 0);
     if (vec4) {
-        if (smem > 48 * 1024)
-            KIRAG_CUDA_OK(cudaFuncSetAttribute(scan_exact_kernel<true>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024 && ensure_dynamic_smem(scan_exact_kernel<true>, smem)) return 1;
         scan_exact_kernel<true><<<(unsigned)blocks, threads, smem, st>>>(master, n, d, q, nq_valid,
                                                                          scores, ld);
     } else {
-        if (smem > 48 * 1024)
-            KIRAG_CUDA_OK(cudaFuncSetAttribute(scan_exact_kernel<false>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024 && ensure_dynamic_smem(scan_exact_kernel<false>, smem)) return 1;
         scan_exact_kernel<false><<<(unsigned)blocks, threads, smem, st>>>(master, n, d, q, nq_valid,
                                                                           scores, ld);
     }

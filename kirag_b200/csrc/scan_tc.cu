@@ -733,7 +733,7 @@ static int launch_scan_pair(const ScanArgs& args_in, int num_sms, cudaStream_t s
     KIRAG_CHECK(ns >= 2, "scan_tc pair: no room for a shared-memory pipeline");
     args.n_stages = ns;
     const size_t smem = fixed + (size_t)ns * kPairStageBytes;
-    KIRAG_CUDA_OK(cudaFuncSetAttribute(scan_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    if (ensure_dynamic_smem(scan_tc_pair_kernel, kSmemLimit)) return 1;
     int64_t pairs = ((args.tile_hi - args.tile_lo + 1) / 2) * ((args.nq + kPairQ - 1) / kPairQ);  // work items
     if (pairs > num_sms / 2) pairs = num_sms / 2;
     if (pairs <= 0) return 0;
@@ -748,8 +748,7 @@ static int launch_scan_t(const ScanArgs& args_in, int num_sms, cudaStream_t st) 
     args.n_stages = pick_stages(BQ, RESIDENT, args.d);
     KIRAG_CHECK(args.n_stages >= 2, "scan_tc: d=%d leaves no room for a shared-memory pipeline", args.d);
     const size_t smem = scan_smem_bytes(BQ, RESIDENT, args.d, args.n_stages);
-    KIRAG_CUDA_OK(cudaFuncSetAttribute(scan_tc_kernel<BQ, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSmemLimit));
+    if (ensure_dynamic_smem(scan_tc_kernel<BQ, RESIDENT>, kSmemLimit)) return 1;
     const int64_t n_qt = (args.nq + BQ - 1) / BQ;
     int64_t grid = (args.tile_hi - args.tile_lo) * n_qt;  // work items
     if (grid > num_sms) grid = num_sms;

@@ -121,6 +121,183 @@ select_pairs_kernel(const Cand* __restrict__ in, int64_t in_stride, const int* _
     }
 }
 
+// ---- between-level compaction: exact top-m SET + m-th value, no sort -----------
+// After a filter level a query's buffer holds the m kept candidates plus the new survivors
+// (a few thousand at most).  The next level only needs (a) the set of the m best and (b) the
+// m-th best score (the new tau) — not their order.  One CTA per query, items in registers:
+//   1. bits on which all score keys agree are taken from the AND of the keys (no counting);
+//   2. the m-th largest SCORE key is found by a bitwise MSB-first selection over the remaining
+//      bits: one block-wide count and ONE barrier per bit;
+//   3. only if several items tie with that score is the same selection run on the row ids of the
+//      tied items (lower row wins, like the final order);
+//   4. the kept items are compacted back to the front of the list (unordered).
+// A few microseconds instead of a 30-50 us bitonic sort of the whole buffer.
+constexpr int kCompactThreads = 1024;
+constexpr int kCompactPerThread = kSelectSeg / kCompactThreads;  // 8
+
+__device__ __forceinline__ int block_sum_1024(int v, int* scratch /* [2][32] */, int parity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane == 0) scratch[parity * 32 + warp] = v;
+    __syncthreads();
+    return __reduce_add_sync(0xffffffffu, scratch[parity * 32 + lane]);
+}
+
+// NS = occupied register slots per thread (compile-time so that the per-bit counting loops carry
+// no dead iterations: the kernel is instruction-issue bound)
+template <int NS>
+__device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q, int raw, int count, int cap, int m,
+                                                  int* __restrict__ cnt, float* __restrict__ tau,
+                                                  int* __restrict__ overflow, int* scratch, unsigned& s_and,
+                                                  unsigned& s_or, unsigned& s_min, int* warp_off) {
+    constexpr int kCompactPerThread = NS;
+    constexpr int n_slots = NS;
+    uint32_t sk[kCompactPerThread];  // score key, 0 = absent (NaN score / empty slot)
+    uint32_t ik[kCompactPerThread];  // 0xffffffff - row: larger = lower row = better
+    if (threadIdx.x == 0) { s_and = 0xffffffffu; s_or = 0u; }
+    int valid_local = 0;
+    unsigned my_and = 0xffffffffu, my_or = 0u;
+#pragma unroll
+    for (int e = 0; e < kCompactPerThread; ++e) {
+        sk[e] = 0u;
+        ik[e] = 0u;
+        if (e < n_slots) {
+            const int i = e * kCompactThreads + threadIdx.x;
+            if (i < count) {
+                const Cand c = list[i];
+                if (c.id >= 0) {
+                    sk[e] = score_key(c.s);
+                    ik[e] = 0xffffffffu - (uint32_t)c.id;
+                }
+            }
+            if (sk[e] != 0u) { ++valid_local; my_and &= sk[e]; my_or |= sk[e]; }
+        }
+    }
+    __syncthreads();
+    my_and = __reduce_and_sync(0xffffffffu, my_and);
+    my_or = __reduce_or_sync(0xffffffffu, my_or);
+    if ((threadIdx.x & 31) == 0) { atomicAnd(&s_and, my_and); atomicOr(&s_or, my_or); }
+    int parity = 0;
+    const int valid = block_sum_1024(valid_local, scratch, parity);  // its barrier also publishes s_and / s_or
+    parity ^= 1;
+    const int keep = valid < m ? valid : m;
+    uint32_t spiv = 0u, ipiv = 0u;  // keep rule: sk > spiv || (sk == spiv && ik >= ipiv); (0,0) keeps every valid item
+    if (valid > m) {
+        const unsigned all_and = s_and, differ = s_and ^ s_or;
+        int kk = m;
+        uint32_t prefix = all_and & ~differ;  // bits shared by every key are decided already
+        for (int b = 31; b >= 0; --b) {
+            if (!((differ >> b) & 1u)) continue;  // block-uniform
+            const uint32_t cand = (prefix | (1u << b)) >> b;
+            int c_local = 0;
+#pragma unroll
+            for (int e = 0; e < kCompactPerThread; ++e)
+                if (e < n_slots) c_local += (sk[e] != 0u && (sk[e] >> b) == cand);
+            const int c = block_sum_1024(c_local, scratch, parity);
+            parity ^= 1;
+            if (c >= kk) prefix |= (1u << b); else kk -= c;
+        }
+        spiv = prefix;  // score key of the m-th best; kk of the items tied at spiv are kept
+        int eq_local = 0;
+#pragma unroll
+        for (int e = 0; e < kCompactPerThread; ++e)
+            if (e < n_slots) eq_local += (sk[e] == spiv);
+        const int n_eq = block_sum_1024(eq_local, scratch, parity);
+        parity ^= 1;
+        if (n_eq > kk) {  // ties straddle rank m: the kk lowest rows among them win
+            uint32_t ipre = 0u;
+            for (int b = 31; b >= 0; --b) {
+                const uint32_t cand = (ipre | (1u << b)) >> b;
+                int c_local = 0;
+#pragma unroll
+                for (int e = 0; e < kCompactPerThread; ++e)
+                    if (e < n_slots) c_local += (sk[e] == spiv && (ik[e] >> b) == cand);
+                const int c = block_sum_1024(c_local, scratch, parity);
+                parity ^= 1;
+                if (c >= kk) ipre |= (1u << b); else kk -= c;
+            }
+            ipiv = ipre;
+        }
+    }
+    // compaction of the kept items back to the front of the list
+    int mine = 0;
+#pragma unroll
+    for (int e = 0; e < kCompactPerThread; ++e)
+        if (e < n_slots) mine += (sk[e] != 0u && (sk[e] > spiv || (sk[e] == spiv && ik[e] >= ipiv)));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_off[warp + 1] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_off[lane + 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        warp_off[lane + 1] = w;
+        if (lane == 0) warp_off[0] = 0;
+    }
+    __syncthreads();
+    int pos = warp_off[warp] + incl - mine;
+#pragma unroll
+    for (int e = 0; e < kCompactPerThread; ++e) {
+        if (e < n_slots && sk[e] != 0u && (sk[e] > spiv || (sk[e] == spiv && ik[e] >= ipiv))) {
+            Cand c;
+            c.s = key_score(sk[e]);
+            c.id = (int32_t)(0xffffffffu - ik[e]);
+            list[pos++] = c;
+        }
+    }
+    // new threshold: the m-th best score, once m items exist
+    if (valid > m) {
+        if (threadIdx.x == 0) tau[q] = key_score(spiv);
+    } else if (valid == m) {
+        // nothing dropped; the m-th best is the minimum: smallest key = AND/OR cannot give it, reduce
+        uint32_t mn = 0xffffffffu;
+#pragma unroll
+        for (int e = 0; e < kCompactPerThread; ++e)
+            if (e < n_slots && sk[e] != 0u && sk[e] < mn) mn = sk[e];
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        if (threadIdx.x == 0) s_min = 0xffffffffu;
+        __syncthreads();
+        if (lane == 0) atomicMin(&s_min, mn);
+        __syncthreads();
+        if (threadIdx.x == 0) tau[q] = key_score(s_min);
+    }
+    if (threadIdx.x == 0) {
+        cnt[q] = keep;
+        if (raw > cap) overflow[q] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cnt, int cap, int m,
+                    float* __restrict__ tau, int* __restrict__ overflow) {
+    __shared__ int scratch[64];
+    __shared__ unsigned s_and, s_or, s_min;
+    __shared__ int warp_off[33];
+    const int q = blockIdx.x;
+    const int raw = cnt[q];
+    const int count = raw > cap ? cap : raw;
+    const int n_slots = (count + kCompactThreads - 1) / kCompactThreads;  // block-uniform
+    Cand* list = buf + (int64_t)q * stride;
+#define KIRAG_COMPACT_CASE(NS) \
+    compact_topm_body<NS>(list, q, raw, count, cap, m, cnt, tau, overflow, scratch, s_and, s_or, s_min, warp_off)
+    if (n_slots <= 1) KIRAG_COMPACT_CASE(1);
+    else if (n_slots == 2) KIRAG_COMPACT_CASE(2);
+    else if (n_slots == 3) KIRAG_COMPACT_CASE(3);
+    else if (n_slots == 4) KIRAG_COMPACT_CASE(4);
+    else if (n_slots <= 6) KIRAG_COMPACT_CASE(6);
+    else KIRAG_COMPACT_CASE(8);
+#undef KIRAG_COMPACT_CASE
+}
+
 // ---- rescored candidates -> D, I (+ certificate) -----------------------------
 // grid nq.  Sorts the (canonical fp32 score, row) pairs, writes the first k as
 // the result row and checks the exactness certificate:
@@ -259,10 +436,7 @@ static int sort_threads(int P) {
 
 template <typename K>
 static int ensure_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
-        KIRAG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)bytes));
-    }
+    if (bytes > 48 * 1024) return ensure_dynamic_smem(kernel, bytes);
     return 0;
 }
 
@@ -296,6 +470,15 @@ int launch_select_pairs(const Cand* in, int64_t in_stride, const int* cnt, int f
     select_pairs_kernel<<<grid, sort_threads(P), smem, st>>>(in, in_stride, cnt, fixed_count, cap, m,
                                                             out, out_stride, tau, cnt_out, overflow);
     KIRAG_LAUNCH_OK("select_pairs_kernel");
+    return 0;
+}
+
+int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, int m, float* tau, int* overflow,
+                        cudaStream_t st) {
+    KIRAG_CHECK(cap <= kSelectSeg && m <= cap, "compact_topm: cap=%d m=%d out of range", cap, m);
+    if (nq <= 0) return 0;
+    compact_topm_kernel<<<(unsigned)nq, kCompactThreads, 0, st>>>(buf, stride, cnt, cap, m, tau, overflow);
+    KIRAG_LAUNCH_OK("compact_topm_kernel");
     return 0;
 }
 

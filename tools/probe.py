@@ -44,6 +44,9 @@ for B in batches:
     per_ms = (ctypes.c_double * 64)()
     per_rows = (ctypes.c_double * 64)()
     lib.kirag_profile_read_launches(per_ms, per_rows, 64)
+    tl_tags = (ctypes.c_int * 512)()
+    tl_ms = (ctypes.c_double * 512)()
+    n_tl = lib.kirag_profile_read_timeline(tl_tags, tl_ms, 512)
     sm, ln, rw = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
     lib.kirag_profile_read(ctypes.byref(sm), ctypes.byref(ln), ctypes.byref(rw))
     lib.kirag_profile_enable(0)
@@ -56,3 +59,9 @@ for B in batches:
     last = [(per_ms[i], per_rows[i]) for i in range(ln.value - nl, ln.value)] if ln.value <= 64 else []
     print("      last step per launch: " + "  ".join(
         f"[{int(r)} rows {m:.3f} ms {r * 2048 / m / 1e6:.0f} GB/s {2.0 * B * r * 1024 / m / 1e9:.0f} TF]" for m, r in last), flush=True)
+    per_step = n_tl // steps if steps else 0
+    if per_step:
+        base = (steps - 1) * per_step
+        t0 = tl_ms[base]
+        print("      timeline (last step, ms since start): " + " ".join(
+            f"{tl_tags[base + i]}:{tl_ms[base + i] - t0:.3f}" for i in range(per_step)), flush=True)
