@@ -23,7 +23,7 @@ namespace kirag {
 
 constexpr int kPoolCluster = 8;
 constexpr int kPoolThreads = 256;
-constexpr int kPoolMaxColsPerThread = 16;  // H <= 256 * 16 = 4096
+constexpr int kPoolMaxColsPerThread = 16;  // H <= 256 * 16 = 4096 (limit checked by the launcher)
 
 template <typename T> struct HiddenLoad;
 template <> struct HiddenLoad<float> {
@@ -83,144 +83,218 @@ __device__ __forceinline__ long long load_mask(const void* mask, int mask_dtype,
     return reinterpret_cast<const unsigned char*>(mask)[idx];
 }
 
-// grid = B * kPoolCluster CTAs, cluster (kPoolCluster,1,1): cluster b <-> batch row b.
-// dynamic smem: int tokens[S] | float partial[Hpad] | float red[kPoolThreads/32 + 2]
-template <typename T, bool VEC>
-__global__ void __cluster_dims__(kPoolCluster, 1, 1) __launch_bounds__(kPoolThreads)
+// 16-byte loads of the hidden states, whatever the dtype (4 fp32 / 8 bf16 / 8 fp16 columns).
+// The raw 16 bytes stay in 4 registers until they are accumulated, so that 8 independent loads
+// per thread are in flight at a modest register cost.
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int kElems = 4;
+    static __device__ __forceinline__ void add(const uint4& raw, float scale, float (&acc)[8]) {
+        acc[0] = fmaf(__uint_as_float(raw.x), scale, acc[0]);
+        acc[1] = fmaf(__uint_as_float(raw.y), scale, acc[1]);
+        acc[2] = fmaf(__uint_as_float(raw.z), scale, acc[2]);
+        acc[3] = fmaf(__uint_as_float(raw.w), scale, acc[3]);
+    }
+};
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int kElems = 8;
+    static __device__ __forceinline__ void add(const uint4& raw, float scale, float (&acc)[8]) {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // bf16 -> fp32 is a 16-bit shift
+            acc[2 * i] = fmaf(__uint_as_float(w[i] << 16), scale, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(__uint_as_float(w[i] & 0xffff0000u), scale, acc[2 * i + 1]);
+        }
+    }
+};
+template <> struct Vec16<__half> {
+    static constexpr int kElems = 8;
+    static __device__ __forceinline__ void add(const uint4& raw, float scale, float (&acc)[8]) {
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            acc[2 * i] = fmaf(t.x, scale, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(t.y, scale, acc[2 * i + 1]);
+        }
+    }
+};
+
+// Cluster of CL CTAs (CL = 1, 2, 4 or 8, chosen at launch so that the grid fills the GPU) owns
+// one batch row.  Shared memory: tokens[S] | ballots[ceil(S/32)] | prefix[ceil(S/32)+1] |
+// partial[R][Hpad] | red[16]
+//   1. all 256 threads scan the mask row in parallel (one ballot per 32 tokens, one warp-level
+//      scan of the ballot popcounts) -> list of kept tokens + denominator (= SUM of mask values,
+//      kept = mask != 0, exactly masked_fill(~mask.bool()) / mask.sum(1); cls: token 0, denom 1)
+//   2. CTA `rank` streams kept tokens rank, rank+CL, ...: the CTA's (token, 16-byte chunk) pairs
+//      are dealt to the threads in order, so every thread issues full 16-byte loads whatever the
+//      dtype and row length; 8 independent loads in flight per thread
+//   3. the partial sums meet in distributed shared memory: CTA `rank` reduces its slice of the
+//      columns over all ranks (and sub-rows), divides, accumulates ||p||^2; a second DSMEM
+//      exchange of the CL shares gives the norm; each CTA normalises and writes its slice.
+// VEC path requires H % kElems == 0 and (256 % TPR == 0 or TPR % 256 == 0), TPR = H / kElems.
+constexpr int kPoolUnroll = 8;
+constexpr int kPoolMaxAcc = 4;  // TPR <= 1024 chunks per row
+
+template <typename T, bool VEC, int NACC>
+__global__ void __launch_bounds__(kPoolThreads)
 pool_normalize_kernel(const T* __restrict__ hidden, const void* __restrict__ mask,
                       float* __restrict__ out, float* __restrict__ pooled_norm, int64_t S, int64_t H,
                       int64_t sb, int64_t ss, int64_t mb, int mask_dtype, int mode, int normalize) {
     cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
-    const int64_t b = blockIdx.x / kPoolCluster;
+    const int64_t b = blockIdx.x / CL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int E = Vec16<T>::kElems;
+    const int64_t Hpad = (H + 7) & ~(int64_t)7;
+    const int n_words = (int)((S + 31) >> 5);
+    const int TPR = VEC ? (int)(H / E) : (int)H;               // 16-byte chunks (or scalars) per token row
+    const int R = VEC ? (TPR >= kPoolThreads ? 1 : kPoolThreads / TPR) : 1;  // token rows per CTA-wide load
     extern __shared__ __align__(16) unsigned char pool_smem[];
-    const int64_t Hpad = (H + 3) & ~(int64_t)3;
     int* tokens = reinterpret_cast<int*>(pool_smem);
-    float* partial = reinterpret_cast<float*>(pool_smem + ((S * 4 + 15) & ~(int64_t)15));
-    float* red = partial + Hpad;
+    unsigned* ballots = reinterpret_cast<unsigned*>(tokens + S);
+    int* prefix = reinterpret_cast<int*>(ballots + n_words);
+    float* partial = reinterpret_cast<float*>(pool_smem + ((((size_t)S + 2 * (size_t)n_words + 1) * 4 + 15) & ~(size_t)15));
+    float* red = partial + (size_t)R * Hpad;
     __shared__ int s_ntok;
     __shared__ float s_denom;
+    __shared__ unsigned long long s_msum;
 
-    // 1. every CTA of the cluster scans the mask row: kept-token list + denominator.
-    //    (mean: denominator is the SUM of the mask values, kept = mask != 0, exactly
-    //     like masked_fill(~mask.bool()) / mask.sum(1); cls: token 0, denominator 1)
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int ntok = 0;
+    // ---- 1. kept-token list ------------------------------------------------------------------
+    if (mode == 1) {
+        if (tid == 0) { tokens[0] = 0; s_ntok = 1; s_denom = 1.0f; }
+        __syncthreads();
+    } else {
+        if (tid == 0) s_msum = 0ull;
+        __syncthreads();
         long long msum = 0;
-        if (mode == 1) {
-            if (lane == 0) tokens[0] = 0;
-            ntok = 1;
-            msum = 1;
-        } else {
-            for (int64_t s0 = 0; s0 < S; s0 += 32) {
-                const int64_t s = s0 + lane;
-                const long long m = (s < S) ? load_mask(mask, mask_dtype, b * mb + s) : 0;
-                msum += m;
-                const unsigned bal = __ballot_sync(0xffffffffu, m != 0);
-                if (m != 0) tokens[ntok + __popc(bal & ((1u << lane) - 1u))] = (int)s;
-                ntok += __popc(bal);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+        for (int64_t s0 = 0; s0 < S; s0 += kPoolThreads) {
+            const int64_t sidx = s0 + tid;
+            const long long mv = (sidx < S) ? load_mask(mask, mask_dtype, b * mb + sidx) : 0;
+            msum += mv;
+            const unsigned bal = __ballot_sync(0xffffffffu, mv != 0);
+            if (lane == 0 && (s0 >> 5) + warp < n_words) ballots[(s0 >> 5) + warp] = bal;
         }
-        if (lane == 0) { s_ntok = ntok; s_denom = (float)msum; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+        if (lane == 0) atomicAdd(&s_msum, (unsigned long long)msum);
+        __syncthreads();
+        if (warp == 0) {
+            int carry = 0;
+            for (int w0 = 0; w0 < n_words; w0 += 32) {
+                const int w = w0 + lane;
+                const int c = (w < n_words) ? __popc(ballots[w]) : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (w < n_words) prefix[w] = carry + incl - c;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) { s_ntok = carry; s_denom = (float)(long long)s_msum; }
+        }
+        __syncthreads();
+        for (int64_t s0 = 0; s0 < S; s0 += kPoolThreads) {
+            const int64_t sidx = s0 + tid;
+            if (sidx < S) {
+                const unsigned bal = ballots[sidx >> 5];
+                if ((bal >> lane) & 1u) tokens[prefix[sidx >> 5] + __popc(bal & ((1u << lane) - 1u))] = (int)sidx;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const int ntok = s_ntok;
 
-    // 2. this CTA sums tokens rank, rank+8, ... ; a thread owns 4 adjacent columns per pass
+    // ---- 2. stream this CTA's tokens ---------------------------------------------------------
     const T* base = hidden + b * sb;
-    float4 acc[kPoolMaxColsPerThread / 4];
+    const int my_ntok = (ntok > rank) ? (ntok - rank + CL - 1) / CL : 0;  // tokens rank, rank+CL, ...
+    if (VEC) {
+        // thread's fixed position inside a token row: chunk(s) c_a = c0 + 256*a, sub-row r (TPR < 256)
+        const int c0 = (TPR >= kPoolThreads) ? tid : tid % TPR;
+        const int r = (TPR >= kPoolThreads) ? 0 : tid / TPR;
+        float acc[NACC][8];
 #pragma unroll
-    for (int i = 0; i < kPoolMaxColsPerThread / 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int n_pass = (int)((Hpad / 4 + kPoolThreads - 1) / kPoolThreads);
-    // 4 tokens per trip so that 4 * n_pass independent 16-byte loads are in flight per thread
-    for (int t0 = rank; t0 < ntok; t0 += 4 * kPoolCluster) {
-        float4 v[4][kPoolMaxColsPerThread / 4];
+        for (int a = 0; a < NACC; ++a)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int t = t0 + u * kPoolCluster;
-            const T* row = base + (int64_t)tokens[t < ntok ? t : t0] * ss;
+            for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+        constexpr int U = kPoolUnroll / NACC;  // tokens in flight per thread (NACC loads each)
+        for (int lt0 = r; lt0 < my_ntok; lt0 += R * U) {
+            uint4 raw[U][NACC];
+            float w[U];
+            // all U*NACC loads are issued unconditionally (a slot past the end re-reads token lt0 with
+            // weight 0), so nothing sits between them and they are all in flight together
 #pragma unroll
-            for (int p = 0; p < kPoolMaxColsPerThread / 4; ++p) {
-                v[u][p] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p < n_pass && t < ntok) {
-                    const int64_t c = ((int64_t)p * kPoolThreads + threadIdx.x) * 4;
-                    if (VEC) {
-                        if (c < H) v[u][p] = HiddenLoad<T>::load4(row + c);
-                    } else {
-                        if (c + 0 < H) v[u][p].x = HiddenLoad<T>::load1(row + c + 0);
-                        if (c + 1 < H) v[u][p].y = HiddenLoad<T>::load1(row + c + 1);
-                        if (c + 2 < H) v[u][p].z = HiddenLoad<T>::load1(row + c + 2);
-                        if (c + 3 < H) v[u][p].w = HiddenLoad<T>::load1(row + c + 3);
-                    }
-                }
+            for (int u = 0; u < U; ++u) {
+                const int lt = lt0 + u * R;
+                const bool ok = lt < my_ntok;
+                w[u] = ok ? 1.0f : 0.0f;
+                const T* row = base + (int64_t)tokens[rank + (ok ? lt : lt0) * CL] * ss + (int64_t)c0 * E;
+#pragma unroll
+                for (int a = 0; a < NACC; ++a)
+                    raw[u][a] = __ldcs(reinterpret_cast<const uint4*>(row + (int64_t)a * kPoolThreads * E));
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) Vec16<T>::add(raw[u][a], w[u], acc[a]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int a = 0; a < NACC; ++a) {
+            float* dst = partial + (size_t)r * Hpad + (size_t)(c0 + a * kPoolThreads) * E;
 #pragma unroll
-            for (int p = 0; p < kPoolMaxColsPerThread / 4; ++p) {
-                acc[p].x += v[u][p].x; acc[p].y += v[u][p].y;
-                acc[p].z += v[u][p].z; acc[p].w += v[u][p].w;
-            }
+            for (int i = 0; i < E; ++i) dst[i] = acc[a][i];
         }
-    }
-#pragma unroll
-    for (int p = 0; p < kPoolMaxColsPerThread / 4; ++p) {
-        if (p < n_pass) {
-            const int64_t c = ((int64_t)p * kPoolThreads + threadIdx.x) * 4;
-            if (c < Hpad) *reinterpret_cast<float4*>(partial + c) = acc[p];
+    } else {
+        // scalar fallback (odd H / unaligned views): thread owns columns tid, tid+256, ...
+        for (int64_t c = tid; c < H; c += kPoolThreads) {
+            float sum = 0.f;
+            for (int t = rank; t < ntok; t += CL) sum += HiddenLoad<T>::load1(base + (int64_t)tokens[t] * ss + c);
+            partial[c] = sum;
         }
     }
     cluster.sync();
 
-    // 3. CTA `rank` reduces its slice of columns over the 8 partials (DSMEM reads),
-    //    divides by the denominator, and accumulates its share of ||p||^2
-    const int64_t cols_per_rank = ((Hpad / 4 + kPoolCluster - 1) / kPoolCluster) * 4;
+    // ---- 3. cross-CTA reduction in distributed shared memory ---------------------------------
+    const int64_t cols_per_rank = ((H + CL - 1) / CL + 3) & ~(int64_t)3;
     const int64_t c_lo = rank * cols_per_rank;
     const int64_t c_hi = (c_lo + cols_per_rank < H) ? (c_lo + cols_per_rank) : H;
     const float denom = s_denom;
     float ss_local = 0.0f;
-    for (int64_t c = c_lo + threadIdx.x; c < c_hi; c += kPoolThreads) {
+    for (int64_t c = c_lo + tid; c < c_hi; c += kPoolThreads) {
         float sum = 0.0f;
-#pragma unroll
-        for (int r = 0; r < kPoolCluster; ++r) {
+        for (int r = 0; r < CL; ++r) {
             const float* peer = cluster.map_shared_rank(partial, r);
-            sum += peer[c];
+            for (int rr = 0; rr < R; ++rr) sum += peer[(size_t)rr * Hpad + c];
         }
         const float pooled = sum / denom;
         ss_local = fmaf(pooled, pooled, ss_local);
-        // stash the pooled value in the (now consumed) local column slot of the output
-        out[b * H + c] = pooled;
+        out[b * H + c] = pooled;  // re-read below by the same thread when normalising
     }
     ss_local = warp_butterfly_sum(ss_local);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss_local;
+    if (lane == 0) red[warp] = ss_local;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         float t = 0.f;
         for (int w = 0; w < kPoolThreads / 32; ++w) t += red[w];
         red[kPoolThreads / 32] = t;  // this CTA's share of the squared norm
     }
     cluster.sync();
-
-    // 4. total norm from the 8 shares, normalise this CTA's slice
-    float total = 0.f;
-#pragma unroll
-    for (int r = 0; r < kPoolCluster; ++r) {
+    float total_ss = 0.f;
+    for (int r = 0; r < CL; ++r) {
         const float* peer = cluster.map_shared_rank(red, r);
-        total += peer[kPoolThreads / 32];
+        total_ss += peer[kPoolThreads / 32];
     }
-    const float nrm = sqrtf(total);
-    if (rank == 0 && threadIdx.x == 0 && pooled_norm) pooled_norm[b] = nrm;
+    const float nrm = sqrtf(total_ss);
+    if (rank == 0 && tid == 0 && pooled_norm) pooled_norm[b] = nrm;
     if (normalize) {
         const float dn = fmaxf(nrm, 1e-12f);
-        for (int64_t c = c_lo + threadIdx.x; c < c_hi; c += kPoolThreads)
-            out[b * H + c] = out[b * H + c] / dn;
+        for (int64_t c = c_lo + tid; c < c_hi; c += kPoolThreads) out[b * H + c] = out[b * H + c] / dn;
     }
-    // peers may still be reading this CTA's shared memory
-    cluster.sync();
+    cluster.sync();  // peers may still be reading this CTA's shared memory
 }
 
 // backward: grad_hidden[b,s,:] = keep(b,s)/denom_b * gp_b,
@@ -284,30 +358,58 @@ pool_normalize_backward_kernel(const float* __restrict__ grad_out, const float* 
     }
 }
 
+template <typename T, bool VEC, int NACC>
+static int pool_launch_cfg(const void* hidden, const void* mask, float* out, float* pooled_norm, int64_t B, int64_t S,
+                           int64_t H, int64_t sb, int64_t ss, int64_t mb, int mask_dtype, int mode, int normalize,
+                           int cl, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024 && ensure_dynamic_smem(pool_normalize_kernel<T, VEC, NACC>, smem)) return 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(B * cl));
+    cfg.blockDim = dim3(kPoolThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const T* hp = (const T*)hidden;
+    KIRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, pool_normalize_kernel<T, VEC, NACC>, hp, mask, out, pooled_norm, S, H, sb, ss, mb,
+                                     mask_dtype, mode, normalize));
+    count_launch();
+    return 0;
+}
+
 template <typename T>
 static int pool_launch_t(const void* hidden, const void* mask, float* out, float* pooled_norm,
                          int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
                          int mask_dtype, int mode, int normalize, cudaStream_t st) {
-    const int64_t Hpad = (H + 3) & ~(int64_t)3;
-    const size_t smem = ((S * 4 + 15) & ~(size_t)15) + (size_t)Hpad * 4 + (kPoolThreads / 32 + 4) * 4;
+    constexpr int E = Vec16<T>::kElems;
+    const int64_t Hpad = (H + 7) & ~(int64_t)7;
+    const int64_t tpr = (H % E == 0) ? H / E : 0;
+    const bool vec = tpr > 0 && tpr <= (int64_t)kPoolThreads * kPoolMaxAcc &&
+                     ((kPoolThreads % tpr == 0) || (tpr % kPoolThreads == 0)) && (sb % E == 0) && (ss % E == 0) &&
+                     ((reinterpret_cast<uintptr_t>(hidden) & 15) == 0);
+    const int R = vec ? (tpr >= kPoolThreads ? 1 : (int)(kPoolThreads / tpr)) : 1;
+    const int64_t n_words = (S + 31) / 32;
+    const size_t smem = ((((size_t)S + 2 * (size_t)n_words + 1) * 4 + 15) & ~(size_t)15) + (size_t)R * Hpad * 4 + 16 * 4;
     KIRAG_CHECK(smem <= 200 * 1024, "pool_normalize: S=%lld H=%lld need %zu B of shared memory",
                 (long long)S, (long long)H, smem);
-    const int vec_elems = 4;
-    const size_t esz = sizeof(T);
-    const bool vec = (H % vec_elems == 0) && (sb % vec_elems == 0) && (ss % vec_elems == 0) &&
-                     ((reinterpret_cast<uintptr_t>(hidden) % (esz * vec_elems)) == 0);
-    const unsigned grid = (unsigned)(B * kPoolCluster);
-    if (vec) {
-        if (smem > 48 * 1024 && ensure_dynamic_smem(pool_normalize_kernel<T, true>, smem)) return 1;
-        pool_normalize_kernel<T, true><<<grid, kPoolThreads, smem, st>>>(
-            (const T*)hidden, mask, out, pooled_norm, S, H, sb, ss, mb, mask_dtype, mode, normalize);
-    } else {
-        if (smem > 48 * 1024 && ensure_dynamic_smem(pool_normalize_kernel<T, false>, smem)) return 1;
-        pool_normalize_kernel<T, false><<<grid, kPoolThreads, smem, st>>>(
-            (const T*)hidden, mask, out, pooled_norm, S, H, sb, ss, mb, mask_dtype, mode, normalize);
-    }
-    KIRAG_LAUNCH_OK("pool_normalize_kernel");
-    return 0;
+    // cluster size: the smallest of 1/2/4/8 that gives at least 4 CTAs per SM's worth of grid
+    int cl = 8;
+    for (int c = 1; c <= 8; c *= 2) if (B * c >= 148 * 4) { cl = c; break; }
+    if (mode == 1) cl = 1;  // CLS: one token per row
+#define KIRAG_POOL_GO(VECF, NACC) \
+    pool_launch_cfg<T, VECF, NACC>(hidden, mask, out, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, cl, smem, st)
+    if (!vec) return KIRAG_POOL_GO(false, 1);
+    const int nacc = tpr >= kPoolThreads ? (int)(tpr / kPoolThreads) : 1;
+    if (nacc == 1) return KIRAG_POOL_GO(true, 1);
+    if (nacc == 2) return KIRAG_POOL_GO(true, 2);
+    if (nacc == 4) return KIRAG_POOL_GO(true, 4);
+    return KIRAG_POOL_GO(false, 1);  // 3 chunks per thread etc.: scalar path
+#undef KIRAG_POOL_GO
 }
 
 int launch_pool_normalize(const void* hidden, const void* mask, float* out, float* pooled_norm,
