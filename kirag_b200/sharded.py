@@ -92,9 +92,14 @@ class ShardedFlatIP:
         if self.world_size == 1:
             return D_loc, I_loc
         nq = q.shape[0]
-        D_all = torch.empty((self.world_size, nq, k), dtype=torch.float32, device=D_loc.device)
-        I_all = torch.empty((self.world_size, nq, k), dtype=torch.int64, device=I_loc.device)
-        # [G*nq, k] views: the concatenated form is what both NCCL and gloo accept
-        dist.all_gather_into_tensor(D_all.view(-1, k), D_loc.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(I_all.view(-1, k), I_loc.contiguous(), group=self.group)
+        # ONE collective for scores and ids: the payload is tiny (12*nq*k bytes per rank), so the
+        # exchange is latency-bound and a second all-gather would double its cost.  Scores ride in
+        # the same int64 tensor as the ids (bit-cast, zero-extended).
+        packed = torch.empty((2, nq, k), dtype=torch.int64, device=I_loc.device)
+        packed[0] = D_loc.contiguous().view(torch.int32).to(torch.int64)
+        packed[1] = I_loc
+        gathered = torch.empty((self.world_size, 2, nq, k), dtype=torch.int64, device=I_loc.device)
+        dist.all_gather_into_tensor(gathered.view(-1, k), packed.view(-1, k), group=self.group)
+        D_all = gathered[:, 0].to(torch.int32).view(torch.float32).contiguous()
+        I_all = gathered[:, 1].contiguous()
         return self.merge_fn(D_all, I_all)
