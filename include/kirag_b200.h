@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define KIRAG_ABI_VERSION 1
+#define KIRAG_ABI_VERSION 2
 
 /* metric ids; only inner product is implemented, as only inner product is
  * ever constructed by the reference (retrieve.py:112, faiss_index_corpus.py:29) */
@@ -62,13 +62,14 @@ typedef struct kirag_index kirag_index_t;
 /* per-call search statistics (all counts are queries unless noted) */
 typedef struct kirag_search_stats {
     int64_t nq;              /* queries in the call */
-    int64_t n_fast;          /* answered by the tcgen05 filter path with a passing certificate */
+    int64_t n_fast;          /* answered by the tcgen05 filter path with a passing certificate (first attempt) */
     int64_t n_exact;         /* answered by the exact fp32 scan (forced, ineligible shape, or escalated) */
     int64_t n_cert_fail;     /* certificate failures observed on the filter path */
     int64_t n_overflow;      /* candidate-buffer overflows observed on the filter path */
     int32_t levels;          /* filter launches (geometric levels) of the last query chunk */
     int32_t path;            /* path actually taken for the bulk of the call (KIRAG_PATH_*) */
     int64_t kernel_launches; /* kernels launched by this library during the call */
+    int64_t n_rescan;        /* certificate failures answered by the second bf16 pass (threshold s_k - eps) */
 } kirag_search_stats_t;
 
 /* ---- library ---------------------------------------------------------- */

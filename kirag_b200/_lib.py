@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkirag_b200.so")
 
 # constants mirrored from the header
-ABI_VERSION = 1
+ABI_VERSION = 2
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 PATH_AUTO, PATH_EXACT, PATH_FAST = 0, 1, 2
@@ -34,6 +34,7 @@ class SearchStats(ctypes.Structure):
         ("levels", c_int32),
         ("path", c_int32),
         ("kernel_launches", c_int64),
+        ("n_rescan", c_int64),
     ]
 
     def as_dict(self):

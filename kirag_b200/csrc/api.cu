@@ -166,7 +166,7 @@ struct kirag_index {
     float maxnorm = 0.f;
     // workspaces (grow-only)
     DevBuf q_dev, D_dev, I_dev, qshadow, qnorm, cand, cnt, tau, overflow, flags, rescored;
-    DevBuf dense, stage_a, stage_b, qmap, qsel;
+    DevBuf dense, stage_a, stage_b, qmap, qsel, qnorm2;
 };
 
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -394,6 +394,63 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     return 0;
 }
 
+// tau2[i] = (k-th canonical score of flagged query i) - eps_i : every row of the true top-k has an
+// approximate score >= tau2 (certificate); a query without k results gets -inf
+__global__ void rescan_threshold_kernel(const float* __restrict__ D, const int* __restrict__ qmap,
+                                        const float* __restrict__ qnorm, int k, float eps_factor, int64_t nb,
+                                        int64_t nb_pad, float* __restrict__ tau2, int* __restrict__ cnt,
+                                        int* __restrict__ overflow) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb_pad) return;
+    if (i >= nb) { tau2[i] = INFINITY; return; }
+    const int q = qmap[i];
+    const float kth = D[(int64_t)q * k + (k - 1)];
+    tau2[i] = (kth > -FLT_MAX) ? kth - eps_factor * qnorm[q] : -INFINITY;
+    cnt[i] = 0;
+    overflow[i] = 0;
+}
+
+// Second chance for queries whose certificate failed: ONE more pass of the bf16 filter over the whole
+// shadow with the provable threshold tau2 = s_k - eps (fixed, no levels), then every collected
+// candidate is rescored in fp32.  Exact by construction; only a buffer overflow (more than `cap`
+// rows within eps of the k-th score) is left to the exact fp32 scan.  qsel: the flagged queries
+// gathered contiguously; qmap: their row numbers in D/I.  still_bad (host) receives the overflowed ones.
+static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_all, int64_t nb, int k, float* D,
+                         int64_t* I, const int* qmap_dev, int64_t id_offset, int cap, std::vector<int>* still_bad,
+                         cudaStream_t st) {
+    const int d = h->d;
+    const int64_t n = h->ntotal;
+    ScanTcPlan plan;
+    if (scan_tc_pick(nb, d, &plan)) return 1;
+    const size_t qs_bytes = scan_tc_qshadow_bytes(nb, d, plan);
+    const int64_t nb_pad = round_up(nb, 256);
+    if (h->qshadow.ensure(qs_bytes)) return 1;
+    if (h->cand.ensure((size_t)nb * cap * sizeof(Cand))) return 1;
+    if (h->cnt.ensure((size_t)nb_pad * 4) || h->tau.ensure((size_t)nb_pad * 4) || h->overflow.ensure((size_t)nb_pad * 4)) return 1;
+    if (h->flags.ensure((size_t)nb_pad * 4)) return 1;
+    if (h->rescored.ensure((size_t)nb * cap * 4)) return 1;
+    const float eps_factor = (float)((ldexp(1.0, -8) * 1.002 + (double)d * ldexp(1.0, -21)) * (double)h->maxnorm);
+    // thresholds from the first-attempt results (still in D), before anything is overwritten
+    rescan_threshold_kernel<<<(unsigned)((nb_pad + 255) / 256), 256, 0, st>>>(
+        D, qmap_dev, qnorm_all, k, eps_factor, nb, nb_pad, h->tau.as<float>(), h->cnt.as<int>(), h->overflow.as<int>());
+    KIRAG_LAUNCH_OK("rescan_threshold_kernel");
+    if ((nb % plan.bq) != 0) KIRAG_CUDA_OK(cudaMemsetAsync(h->qshadow.p, 0, qs_bytes, st));
+    if (launch_convert_rows(qsel, nb, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, nullptr, st)) return 1;
+    const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+    if (launch_scan_tc(h->shadow, n, d, h->qshadow.p, nb, plan, 0, n_tiles, n_tiles, 1, h->tau.as<float>(),
+                       h->cand.as<Cand>(), h->cnt.as<int>(), cap, h->num_sms, st)) return 1;
+    if (launch_rescore(h->master, d, qsel, h->cand.as<Cand>(), h->cnt.as<int>(), cap, cap, h->rescored.as<float>(), nb, st)) return 1;
+    // overflow = appended count beyond the buffer
+    std::vector<int> counts((size_t)nb);
+    KIRAG_CUDA_OK(cudaMemcpyAsync(counts.data(), h->cnt.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    if (launch_final(h->cand.as<Cand>(), cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, cap, (int)nb, k, D, I,
+                     id_offset, nullptr, nullptr, 0.f, 0, nullptr, nullptr, qmap_dev, st)) return 1;
+    KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < nb; ++i)
+        if (counts[(size_t)i] > cap) still_bad->push_back((int)i);
+    return 0;
+}
+
 static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float* D, int64_t* I,
                        int ptrs_are_device, int64_t id_offset, int path, kirag_search_stats_t* stats,
                        cudaStream_t st) {
@@ -410,7 +467,7 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
     const long long launches0 = g_launches.load();
     const int d = h->d;
     const int64_t kQChunk = 16384;
-    int64_t n_fast = 0, n_exact = 0, n_cert_fail = 0, n_overflow = 0;
+    int64_t n_fast = 0, n_exact = 0, n_cert_fail = 0, n_overflow = 0, n_rescan = 0;
     int levels = 0;
     FastParams fp{};
     const bool fast_ok = (path != KIRAG_PATH_EXACT) && h->ntotal > 0 && fast_eligible(h, k, &fp);
@@ -448,17 +505,39 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
                 if (flags[i]) { bad.push_back((int)i); if (!ovf[i]) ++n_cert_fail; }
             }
             if (!bad.empty() && path == KIRAG_PATH_AUTO) {
-                const int64_t nb = (int64_t)bad.size();
-                if (h->qmap.ensure((size_t)nb * 4)) return 1;
-                if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
-                KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-                gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
-                KIRAG_LAUNCH_OK("gather_rows_kernel");
-                if (exact_search(h, h->qsel.as<float>(), nb, k, Dd, Id, 0, h->qmap.as<int>(), id_offset, st)) return 1;
-                // bad[] lives on the host stack frame until the copy above has been consumed
-                KIRAG_CUDA_OK(cudaStreamSynchronize(st));
-                n_exact += nb;
-                n_fast += cq - nb;
+                // 1st escalation: certificate failures (not overflows) get one more bf16 pass with the
+                // provable threshold; 2nd: whatever is left goes to the exact fp32 scan
+                std::vector<int> rescan, exact;
+                for (int b : bad) (ovf[(size_t)b] || env_int("KIRAG_NO_RESCAN", 0) ? exact : rescan).push_back(b);
+                if (!rescan.empty()) {
+                    const int64_t nb = (int64_t)rescan.size();
+                    if (h->qmap.ensure((size_t)nb * 4)) return 1;
+                    if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
+                    if (h->qnorm2.ensure((size_t)cq * 4)) return 1;
+                    // qnorm / flags buffers are reused by the rescan: keep a copy of the norms
+                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qnorm2.p, h->qnorm.p, (size_t)cq * 4, cudaMemcpyDeviceToDevice, st));
+                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, rescan.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+                    gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
+                    KIRAG_LAUNCH_OK("gather_rows_kernel");
+                    std::vector<int> still_bad;
+                    if (rescan_search(h, h->qsel.as<float>(), h->qnorm2.as<float>(), nb, k, Dd, Id, h->qmap.as<int>(),
+                                      id_offset, kSelectSeg, &still_bad, st)) return 1;
+                    for (int i : still_bad) exact.push_back(rescan[(size_t)i]);
+                    n_rescan += nb - (int64_t)still_bad.size();
+                }
+                if (!exact.empty()) {
+                    const int64_t nb = (int64_t)exact.size();
+                    if (h->qmap.ensure((size_t)nb * 4)) return 1;
+                    if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
+                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, exact.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+                    gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
+                    KIRAG_LAUNCH_OK("gather_rows_kernel");
+                    if (exact_search(h, h->qsel.as<float>(), nb, k, Dd, Id, 0, h->qmap.as<int>(), id_offset, st)) return 1;
+                    // exact[] lives on the host stack frame until the copy above has been consumed
+                    KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+                    n_exact += nb;
+                }
+                n_fast += cq - (int64_t)bad.size();
             } else {
                 n_fast += cq;
             }
@@ -475,6 +554,7 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
         stats->n_exact = n_exact;
         stats->n_cert_fail = n_cert_fail;
         stats->n_overflow = n_overflow;
+        stats->n_rescan = n_rescan;
         stats->levels = levels;
         stats->path = fast_ok ? path : KIRAG_PATH_EXACT;
         stats->kernel_launches = g_launches.load() - launches0;
@@ -600,7 +680,7 @@ int kirag_index_destroy(kirag_index_t* h) {
     if (h->shadow) cudaFree(h->shadow);
     if (h->maxnorm2_bits) cudaFree(h->maxnorm2_bits);
     DevBuf* bufs[] = {&h->q_dev, &h->D_dev, &h->I_dev, &h->qshadow, &h->qnorm, &h->cand, &h->cnt, &h->tau,
-                      &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel};
+                      &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel, &h->qnorm2};
     for (DevBuf* b : bufs) b->release();
     delete h;
     return 0;

@@ -172,17 +172,35 @@ def test_duplicates_lower_id_wins(fa):
                 assert ids[a] < ids[a + 1]
 
 
-def test_clustered_data_escalates_and_stays_exact(fa):
-    """Tight clusters: rank-k and rank-4k scores are closer than the bf16 error bound, so the
-    certificate must fail and the exact scan must answer — results stay exact."""
+def test_clustered_data_escalates_and_stays_exact(fa, monkeypatch):
+    """Clusters: rank-k and rank-4k scores are closer than the bf16 error bound, so the certificate
+    must fail.  First escalation = one more bf16 pass with the provable threshold s_k - eps
+    (n_rescan); if more rows than the buffer holds lie within eps, the exact fp32 scan answers
+    (n_exact).  Results stay exact either way."""
     rng = np.random.default_rng(7)
     centers = unit_rows(rng, 8, 128)
-    xb = centers[rng.integers(0, 8, 20000)] + 1e-4 * rng.standard_normal((20000, 128)).astype(np.float32)
+    # moderately tight clusters: a few hundred rows within eps of the k-th score -> rescan succeeds
+    xb = centers[rng.integers(0, 8, 40000)] + 0.004 * rng.standard_normal((40000, 128)).astype(np.float32)
     xb = (xb / np.linalg.norm(xb, axis=1, keepdims=True)).astype(np.float32)
-    xq = centers[:4]
-    D, I, st = build(fa, xb).search_ex(xq, 10, path=AUTO)
-    assert st["n_exact"] >= 1, st
+    xq = (centers[:4] + 0.01 * unit_rows(rng, 4, 128)).astype(np.float32)
+    ix = build(fa, xb)
+    D, I, st = ix.search_ex(xq, 10, path=AUTO)
+    assert st["n_cert_fail"] >= 1 and st["n_rescan"] + st["n_exact"] == st["n_cert_fail"] + st["n_overflow"], st
+    assert st["n_rescan"] >= 1, st
     assert_topk_parity(D, I, xb, xq, 10, what=f"clustered {st}")
+    De, Ie, _ = ix.search_ex(xq, 10, path=EXACT)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De)
+    # degenerate clusters: thousands of rows within eps -> the rescan buffer overflows -> exact scan
+    xb2 = centers[rng.integers(0, 8, 80000)] + 1e-5 * rng.standard_normal((80000, 128)).astype(np.float32)
+    xb2 = (xb2 / np.linalg.norm(xb2, axis=1, keepdims=True)).astype(np.float32)
+    D, I, st = build(fa, xb2).search_ex(centers[:3], 10, path=AUTO)
+    assert st["n_exact"] >= 1, st
+    assert_topk_parity(D, I, xb2, centers[:3], 10, what=f"degenerate clusters {st}")
+    # the rescan can be switched off: the same queries then go straight to the exact scan
+    monkeypatch.setenv("KIRAG_NO_RESCAN", "1")
+    D2, I2, st2 = ix.search_ex(xq, 10, path=AUTO)
+    assert st2["n_rescan"] == 0 and st2["n_exact"] >= 1, st2
+    assert np.array_equal(I2, Ie) and np.array_equal(D2, De)
 
 
 def test_sorted_corpus_is_not_pathological(fa):
