@@ -96,3 +96,43 @@ def test_ixfi_container_layout(tmp_path):
     assert int.from_bytes(raw[16:24], "little") == 1 << 20 and raw[32] == 1
     assert int.from_bytes(raw[33:37], "little") == 0 and int.from_bytes(raw[37:45], "little") == 12
     assert np.array_equal(np.frombuffer(raw[45:], dtype="<f4"), np.arange(12, dtype=np.float32))
+
+
+def test_embedding_shard_writer_matches_reference_file_format(tmp_path):
+    """compute_corpus_embeddings.py:114-115 file pairs, written per rank without any collective, are
+    consumed by the (exact-pairing) index builder's file discovery in ascending order."""
+    import torch
+
+    from kirag_b200.embed_writer import ContiguousShardSampler, EmbeddingShardWriter
+
+    n, d, per_file, world = 2500, 8, 1000, 2
+    emb = torch.arange(n * d, dtype=torch.float32).reshape(n, d)
+    ids = [str(7 * i) for i in range(n)]
+    for rank in range(world):
+        sampler = ContiguousShardSampler(n, rank, world)
+        w = EmbeddingShardWriter(str(tmp_path), d, sampler.lo, sampler.hi, ids, num_passage_per_index_file=per_file)
+        rows = list(sampler)
+        for i in range(0, len(rows), 96):  # batches that straddle file boundaries
+            b = rows[i:i + 96]
+            w.add(b, emb[b])
+        w.close()
+    pairs = build_index.pair_embedding_files(str(tmp_path))
+    names = [os.path.basename(a) for a, _ in pairs]
+    assert names == ["corpus_embeddings_0_999.pkl", "corpus_embeddings_1000_1249.pkl",
+                     "corpus_embeddings_1250_1999.pkl", "corpus_embeddings_2000_2499.pkl"]
+    got_e, got_i = [], []
+    for a, b in pairs:
+        t = pickle.load(open(a, "rb"))
+        assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and not t.is_cuda
+        got_e.append(t)
+        got_i += pickle.load(open(b, "rb"))
+    assert torch.equal(torch.cat(got_e), emb) and got_i == ids
+
+
+def test_contiguous_sampler_covers_everything_once():
+    from kirag_b200.embed_writer import ContiguousShardSampler
+
+    for n in (0, 5, 1001):
+        for world in (1, 3, 8):
+            seen = [i for r in range(world) for i in ContiguousShardSampler(n, r, world)]
+            assert seen == list(range(n))
