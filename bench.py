@@ -259,7 +259,14 @@ def measure_batch(sh, lib, q_all, batch, k, steps, warmup, device, dist_ok, peak
         ach = flops_alg / (scan_ms_step * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"]}
-    roof.update({"traffic": None, "kernel": "scan_tc_kernel", "kernel_ms_per_step": scan_ms_step,
+    # dram__bytes_read.sum + dram__bytes_write.sum of the scan launches of one step, from the committed
+    # `ncu --set full` capture of this very workload (profiles/r01_scan_traffic.json); null otherwise
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
+    if world == 1 and rows_total == 21_000_000 and k == 100 and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(str(batch), {}).get("dram_bytes_per_step")
+    roof.update({"traffic": traffic, "traffic_note": "bytes per step (all scan launches of one step), ncu capture",
+                 "kernel": "scan_tc_pair_kernel" if batch > 128 else "scan_tc_kernel", "kernel_ms_per_step": scan_ms_step,
                  "kernel_share_of_step": scan_ms_step / ms if ms > 0 else None,
                  "launches_per_step": launches.value / steps, "peak_source": peaks["source"],
                  "algorithmic_bytes_per_step": bytes_alg, "algorithmic_flops_per_step": flops_alg,

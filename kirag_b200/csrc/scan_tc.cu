@@ -217,6 +217,7 @@ struct ScanArgs {
     int* cnt;          // [nq]
     int cap;
     int n_stages;
+    int x_policy;      // L2 policy of corpus blocks that are re-read per query tile: 1 normal, 2 evict_last
     float* dump;       // optional [n_rows, dump_ld] dense approx scores (debug / tests)
     int64_t dump_ld;
 };
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
     if (warp == 0) {
         // =============================== producer ===============================
         if (lane == 0) {
-            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : policy_evict_normal();
+            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy == 2 ? policy_evict_last() : policy_evict_normal());
             const uint64_t pol_q = policy_evict_last();
             if (RESIDENT) {
                 mbar_expect_tx(q_bar, (uint32_t)(KC * kQBlockBytes));
@@ -578,7 +579,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
     if (warp == 0) {
         // =============================== producer ===============================
         if (lane == 0) {
-            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : policy_evict_normal();
+            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy == 2 ? policy_evict_last() : policy_evict_normal());
             const uint64_t pol_q = policy_evict_last();
             int s = 0;
             uint32_t ph = 0;
@@ -788,6 +789,7 @@ int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshado
     args.cap = cap;
     args.dump = nullptr;
     args.dump_ld = 0;
+    args.x_policy = env_flag("KIRAG_X_POLICY", 2);  // evict_last measured ~2% faster at batch 4096 (less HBM re-read)
     return launch_scan_args(args, plan, num_sms, st);
 }
 
