@@ -179,7 +179,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------ our arm ---
@@ -345,9 +345,15 @@ def run_ours(args):
                           "n_fast": r["stats"].get("n_fast"), "n_exact": r["stats"].get("n_exact")})
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the CPU leg runs in its own process (own thread-pool settings), through the reference arm
         try:
-            _, cpu, _ = cpu_baseline(B, k, args.rows, args.cpu_sample_rows or (1 << 18), steps=1, warmup=0)
+            env = {k_: v for k_, v in os.environ.items() if not k_.endswith("_NUM_THREADS")}
+            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                   "--warmup", "0", "--batch", str(B), "--k", str(k), "--rows", str(args.rows),
+                                   "--cpu-sample-rows", str(args.cpu_sample_rows or (1 << 18))],
+                                  capture_output=True, text=True, timeout=600, env=env)
+            cpu = json.loads(proc.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as exc:  # the baseline is a reported number, never a reason to lose the line
             cpu = {"value": None, "unit": "queries/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
                    "sample": f"failed: {exc}"}
@@ -371,15 +377,34 @@ def run_ours(args):
             "search_stats": head["stats"],
             "sweep": sweep_out,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist_ok:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) to stderr."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # libraries (NCCL's version banner, for one) print to fd 1: keep the contract's single JSON line clean
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core (set before torch/numpy load)
+        cores = str(len(os.sched_getaffinity(0)))
+        for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ[var] = cores
         run_reference(args)
     else:
         run_ours(args)
