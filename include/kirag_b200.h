@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define KIRAG_ABI_VERSION 2
+#define KIRAG_ABI_VERSION 3
 
 /* metric ids; only inner product is implemented, as only inner product is
  * ever constructed by the reference (retrieve.py:112, faiss_index_corpus.py:29) */
@@ -164,6 +164,34 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
  * padding).  Used after the NCCL all-gather of the row-sharded search. */
 int kirag_merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t nq, int k,
                      float* D_out, int64_t* I_out, int ptrs_are_device, int device, void* stream);
+
+/* ---- peer-memory exchange of the row-sharded search (one process per GPU) ---
+ * Replaces "NCCL all-gather of the per-shard [nq,k] results + kirag_merge_topk" by ONE kernel per
+ * rank that stores its result rows into every rank's exchange buffer over NVLink (buffers mapped
+ * with CUDA IPC), waits per query range for the other ranks' rows and merges them.  No counterpart
+ * in the reference (FAISS search is single-process CPU, retriever/index.py:47).
+ * SPMD contract: every rank makes the same sequence of kirag_exchange_merge_topk calls with the
+ * same nq and k.  The 64-byte IPC handles are exchanged by the host (torch.distributed). */
+typedef struct kirag_exchange kirag_exchange_t;
+
+/* Allocate this rank's exchange buffer: capacity max_nq*max_k result entries per rank and parity. */
+int kirag_exchange_create(int device, int rank, int world, int64_t max_nq, int max_k, kirag_exchange_t** out);
+int kirag_exchange_destroy(kirag_exchange_t* x);
+/* sizeof(cudaIpcMemHandle_t) (64) */
+int kirag_exchange_handle_bytes(void);
+/* Write this rank's IPC handle (kirag_exchange_handle_bytes() bytes) to handle_out. */
+int kirag_exchange_export(kirag_exchange_t* x, void* handle_out);
+/* handles_all: world * kirag_exchange_handle_bytes() bytes, rank-major; maps every peer's buffer. */
+int kirag_exchange_connect(kirag_exchange_t* x, const void* handles_all);
+/* Same with raw device pointers (ranks living in one process: peer_buffers[g] = kirag_exchange_buffer
+ * of rank g; entry [rank] is ignored). */
+int kirag_exchange_connect_ptrs(kirag_exchange_t* x, void* const* peer_buffers);
+void* kirag_exchange_buffer(kirag_exchange_t* x);
+/* D_loc/I_loc: this rank's per-shard result [nq,k] (device, rows sorted by (score desc, id asc), global
+ * ids, padding id -1); D_out/I_out: the global top-k [nq,k] (device), identical on every rank.
+ * Stream-ordered; the kernel spins (bounded, ~20 s) until every peer's call has delivered. */
+int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, int64_t nq, int k,
+                              float* D_out, int64_t* I_out, void* stream);
 
 /* torch.topk(torch.matmul(Q, T.T), k, dim=1)   knowledge_graph/models.py:1532-1538
  * One-shot search over a transient candidate matrix T [nt, d] (device or host

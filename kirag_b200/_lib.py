@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkirag_b200.so")
 
 # constants mirrored from the header
-ABI_VERSION = 2
+ABI_VERSION = 3
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 PATH_AUTO, PATH_EXACT, PATH_FAST = 0, 1, 2
@@ -70,6 +70,14 @@ SIGNATURES = {
     "kirag_index_device_ptrs": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     "kirag_index_debug_scores": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "kirag_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "kirag_exchange_create": (c_int, [c_int, c_int, c_int, c_int64, c_int, POINTER(c_void_p)]),
+    "kirag_exchange_destroy": (c_int, [c_void_p]),
+    "kirag_exchange_handle_bytes": (c_int, []),
+    "kirag_exchange_export": (c_int, [c_void_p, c_void_p]),
+    "kirag_exchange_connect": (c_int, [c_void_p, c_void_p]),
+    "kirag_exchange_connect_ptrs": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "kirag_exchange_buffer": (c_void_p, [c_void_p]),
+    "kirag_exchange_merge_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "kirag_topk_ip": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                               c_void_p]),
     "kirag_pool_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,

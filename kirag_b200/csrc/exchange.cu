@@ -1,0 +1,344 @@
+// exchange.cu — fused peer-memory exchange + merge of the row-sharded search.
+//
+// No counterpart in the reference (its FAISS search is single-process CPU,
+// /root/reference/retriever/index.py:47).  After the per-shard search every rank holds the exact
+// top-k of ITS rows for every query; the global answer is the top-k of the union.  Instead of an
+// NCCL all-gather followed by a merge kernel, ONE kernel per rank does both over NVLink peer
+// memory (buffers mapped with CUDA IPC, one process per GPU):
+//   push   : CTA b stores the result rows of its query range [q_lo, q_hi) into slot `rank` of
+//            EVERY rank's exchange buffer (plain coalesced stores; remote ones travel over NVLink),
+//            then publishes flag[rank][b] = epoch in every rank's buffer (release, system scope);
+//   wait   : CTA b polls its OWN flags[g][b] (acquire, system scope) until all G ranks have
+//            delivered that query range — there is no grid-wide or GPU-wide barrier, a query
+//            range is merged as soon as its G pieces are there;
+//   merge  : the G lists are sorted by (score desc, id asc) and hold distinct ids, so the global
+//            rank of an item is the number of items that precede it in each list: G binary
+//            searches per item, no sort, no barrier.  Items of rank < k are written out.
+// Buffers are double-buffered by epoch parity: a rank can be at most one call ahead of its peers
+// (it cannot finish call e before every peer has STARTED call e, i.e. finished call e-1), so
+// data of call e+1 never lands in a slot that call e-1 is still reading.
+// Every CTA pushes before it waits and the grid is small enough to be co-resident, so the wait
+// cannot deadlock; it is bounded anyway (trap after ~20 s) so that a dead peer is an error, not
+// a hang.
+#include "common.cuh"
+#include "../../include/kirag_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace kirag {
+
+constexpr int kMaxRanks = 16;
+constexpr int kExchangeMaxBlocks = 296;  // flags per (parity, source rank); 2 CTAs per SM on 148 SMs
+
+struct ExchangeArgs {
+    uint8_t* peer[kMaxRanks];  // exchange buffer of every rank as mapped in THIS process (peer[rank] = own)
+    int rank, G;
+    int64_t nq;
+    int k;
+    int parity;
+    int epoch;
+    size_t slot_bytes;   // capacity of one (parity, source rank) slot
+    size_t flags_off;    // byte offset of the flag region
+    size_t ids_off;      // byte offset of the id block inside a slot for this call (after nq*k scores)
+    const float* D_loc;
+    const int64_t* I_loc;
+    float* D_out;
+    int64_t* I_out;
+};
+
+__device__ __forceinline__ uint8_t* slot_ptr(const ExchangeArgs& a, int dst, int src) {
+    return a.peer[dst] + ((size_t)a.parity * a.G + src) * a.slot_bytes;
+}
+__device__ __forceinline__ int* flag_ptr(const ExchangeArgs& a, int dst, int src, int block) {
+    return reinterpret_cast<int*>(a.peer[dst] + a.flags_off) + ((size_t)a.parity * kMaxRanks + src) * kExchangeMaxBlocks + block;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// (key, id) total order of the result lists: larger key first, then lower id
+__device__ __forceinline__ bool item_before(uint32_t ka, int64_t ia, uint32_t kb, int64_t ib) {
+    return (ka > kb) || (ka == kb && ia < ib);
+}
+
+// number of items of the sorted list (keys[0..n), ids[0..n)) that come before (key, id)
+__device__ __forceinline__ int count_before(const uint32_t* keys, const int64_t* ids, int n, uint32_t key, int64_t id) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (item_before(keys[mid], ids[mid], key, id)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(512, 2) exchange_merge_kernel(const ExchangeArgs a) {
+    extern __shared__ uint64_t xsmem[];
+    const int G = a.G, k = a.k;
+    int64_t* ids = reinterpret_cast<int64_t*>(xsmem);            // [G * k]
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ids + G * k);   // [G * k]
+    __shared__ int n_valid[kMaxRanks];
+    const int b = blockIdx.x, NB = gridDim.x;
+    const int64_t q_lo = a.nq * b / NB, q_hi = a.nq * (b + 1) / NB;
+    const int64_t e_lo = q_lo * k, e_hi = q_hi * k;
+
+    // ------------------------------------------------------------------ push ----
+    // peers are visited in a rank-rotated order so that the G ranks do not all hit the same
+    // destination at the same time
+    for (int p = 0; p < G; ++p) {
+        const int dst = (a.rank + p) % G;
+        uint8_t* slot = slot_ptr(a, dst, a.rank);
+        float* sd = reinterpret_cast<float*>(slot);
+        int64_t* si = reinterpret_cast<int64_t*>(slot + a.ids_off);
+        for (int64_t i = e_lo + threadIdx.x; i < e_hi; i += blockDim.x) {
+            sd[i] = a.D_loc[i];
+            si[i] = a.I_loc[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        // the barrier above ordered every thread's stores before this fence (cumulativity)
+        __threadfence_system();
+        st_release_sys(flag_ptr(a, threadIdx.x, a.rank, b), a.epoch);
+    }
+    // ------------------------------------------------------------------ wait ----
+    if (threadIdx.x < G) {
+        const int* f = flag_ptr(a, a.rank, threadIdx.x, b);
+        if (ld_acquire_sys(f) != a.epoch) {
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) != a.epoch) {
+                __nanosleep(64);
+                if (clock64() - t0 > 40000000000LL) {
+                    printf("kirag exchange: rank %d block %d timed out waiting for rank %d (epoch %d, flag %d)\n",
+                           a.rank, b, (int)threadIdx.x, a.epoch, ld_acquire_sys(f));
+                    __trap();
+                }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    // ----------------------------------------------------------------- merge ----
+    const int L = G * k;
+    for (int64_t q = q_lo; q < q_hi; ++q) {
+        if (threadIdx.x < G) n_valid[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+            const int g = i / k, j = i - g * k;
+            const uint8_t* slot = slot_ptr(a, a.rank, g);
+            const int64_t id = __ldcg(reinterpret_cast<const int64_t*>(slot + a.ids_off) + q * k + j);
+            uint32_t key = 0u;
+            if (id >= 0) key = score_key(__ldcg(reinterpret_cast<const float*>(slot) + q * k + j));
+            const bool ok = key != 0u;
+            keys[i] = key;
+            ids[i] = ok ? id : INT64_MAX;
+            if (ok) atomicAdd(&n_valid[g], 1);  // valid items form a prefix of each list
+        }
+        __syncthreads();
+        int total = 0;
+        for (int g = 0; g < G; ++g) total += n_valid[g];
+        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+            const int g = i / k, j = i - g * k;
+            if (j >= n_valid[g]) continue;
+            const uint32_t key = keys[i];
+            const int64_t id = ids[i];
+            int r = j;  // items of its own list that precede it
+            for (int h = 0; h < G; ++h)
+                if (h != g) r += count_before(keys + h * k, ids + h * k, n_valid[h], key, id);
+            if (r < k) {
+                a.D_out[q * k + r] = key_score(key);
+                a.I_out[q * k + r] = id;
+            }
+        }
+        for (int j = total + threadIdx.x; j < k; j += blockDim.x) {  // fewer than k results in total
+            a.D_out[q * k + j] = -FLT_MAX;
+            a.I_out[q * k + j] = -1;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace kirag
+
+using namespace kirag;
+
+struct kirag_exchange {
+    int device = 0;
+    int rank = 0;
+    int world = 1;
+    int64_t max_nq = 0;
+    int max_k = 0;
+    size_t slot_bytes = 0;
+    size_t flags_off = 0;
+    size_t total_bytes = 0;
+    uint8_t* own = nullptr;
+    uint8_t* peer[kMaxRanks] = {nullptr};
+    bool opened[kMaxRanks] = {false};  // mapped with cudaIpcOpenMemHandle (to be closed)
+    bool connected = false;
+    int epoch = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+namespace {
+struct DeviceGuardLite {
+    int prev = -1;
+    explicit DeviceGuardLite(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuardLite() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
+extern "C" {
+
+int kirag_exchange_create(int device, int rank, int world, int64_t max_nq, int max_k, kirag_exchange_t** out) {
+    KIRAG_CHECK(out != nullptr, "exchange_create: null out pointer");
+    *out = nullptr;
+    KIRAG_CHECK(world >= 1 && world <= kMaxRanks, "exchange_create: world size %d not in [1, %d]", world, kMaxRanks);
+    KIRAG_CHECK(rank >= 0 && rank < world, "exchange_create: rank %d not in [0, %d)", rank, world);
+    KIRAG_CHECK(max_nq > 0 && max_k > 0, "exchange_create: max_nq and max_k must be positive");
+    KIRAG_CHECK((int64_t)world * max_k <= 8192, "exchange_create: world*max_k=%lld exceeds 8192",
+                (long long)world * max_k);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    KIRAG_CUDA_OK(cudaSetDevice(device));
+    kirag_exchange* x = new (std::nothrow) kirag_exchange();
+    KIRAG_CHECK(x != nullptr, "exchange_create: out of host memory");
+    x->device = device;
+    x->rank = rank;
+    x->world = world;
+    x->max_nq = max_nq;
+    x->max_k = max_k;
+    x->slot_bytes = align_up((size_t)max_nq * max_k * 4, 16) + align_up((size_t)max_nq * max_k * 8, 16);
+    x->flags_off = align_up(2 * (size_t)world * x->slot_bytes, 256);
+    x->total_bytes = x->flags_off + 2 * (size_t)kMaxRanks * kExchangeMaxBlocks * sizeof(int);
+    cudaError_t e = cudaMalloc((void**)&x->own, x->total_bytes);
+    if (e != cudaSuccess) {
+        set_error("exchange_create: cudaMalloc(%zu) failed: %s", x->total_bytes, cudaGetErrorString(e));
+        delete x;
+        if (prev >= 0) cudaSetDevice(prev);
+        return 1;
+    }
+    e = cudaMemset(x->own, 0, x->total_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        set_error("exchange_create: clearing the buffer failed: %s", cudaGetErrorString(e));
+        cudaFree(x->own);
+        delete x;
+        if (prev >= 0) cudaSetDevice(prev);
+        return 1;
+    }
+    x->peer[rank] = x->own;
+    if (world == 1) x->connected = true;
+    if (prev >= 0) cudaSetDevice(prev);
+    *out = x;
+    return 0;
+}
+
+int kirag_exchange_destroy(kirag_exchange_t* x) {
+    if (!x) return 0;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < x->world; ++g)
+        if (x->opened[g] && x->peer[g]) cudaIpcCloseMemHandle(x->peer[g]);
+    if (x->own) cudaFree(x->own);
+    delete x;
+    if (prev >= 0) cudaSetDevice(prev);
+    return 0;
+}
+
+int kirag_exchange_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int kirag_exchange_export(kirag_exchange_t* x, void* handle_out) {
+    KIRAG_CHECK(x && handle_out, "exchange_export: null argument");
+    DeviceGuardLite guard(x->device);
+    cudaIpcMemHandle_t h;
+    KIRAG_CUDA_OK(cudaIpcGetMemHandle(&h, x->own));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int kirag_exchange_connect(kirag_exchange_t* x, const void* handles_all) {
+    KIRAG_CHECK(x && handles_all, "exchange_connect: null argument");
+    KIRAG_CHECK(!x->connected || x->world == 1, "exchange_connect: already connected");
+    DeviceGuardLite guard(x->device);
+    const uint8_t* hp = static_cast<const uint8_t*>(handles_all);
+    for (int g = 0; g < x->world; ++g) {
+        if (g == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hp + (size_t)g * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("exchange_connect: cudaIpcOpenMemHandle for rank %d failed: %s", g, cudaGetErrorString(e));
+            cudaGetLastError();
+            return 1;
+        }
+        x->peer[g] = static_cast<uint8_t*>(p);
+        x->opened[g] = true;
+    }
+    x->connected = true;
+    return 0;
+}
+
+int kirag_exchange_connect_ptrs(kirag_exchange_t* x, void* const* peer_buffers) {
+    KIRAG_CHECK(x && peer_buffers, "exchange_connect_ptrs: null argument");
+    for (int g = 0; g < x->world; ++g) {
+        if (g == x->rank) continue;
+        KIRAG_CHECK(peer_buffers[g] != nullptr, "exchange_connect_ptrs: null buffer for rank %d", g);
+        x->peer[g] = static_cast<uint8_t*>(peer_buffers[g]);
+    }
+    x->connected = true;
+    return 0;
+}
+
+void* kirag_exchange_buffer(kirag_exchange_t* x) { return x ? x->own : nullptr; }
+
+int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, int64_t nq, int k,
+                              float* D_out, int64_t* I_out, void* stream) {
+    KIRAG_CHECK(x != nullptr, "exchange_merge: null exchange");
+    KIRAG_CHECK(x->connected, "exchange_merge: peers are not connected (call kirag_exchange_connect first)");
+    KIRAG_CHECK(k > 0 && k <= x->max_k, "exchange_merge: k=%d not in [1, %d]", k, x->max_k);
+    KIRAG_CHECK(nq >= 0 && nq * (int64_t)k <= x->max_nq * (int64_t)x->max_k,
+                "exchange_merge: nq*k=%lld exceeds the capacity %lld", (long long)(nq * k),
+                (long long)(x->max_nq * x->max_k));
+    if (nq == 0) return 0;
+    KIRAG_CHECK(D_loc && I_loc && D_out && I_out, "exchange_merge: null buffer");
+    DeviceGuardLite guard(x->device);
+    ExchangeArgs a{};
+    for (int g = 0; g < x->world; ++g) a.peer[g] = x->peer[g];
+    a.rank = x->rank;
+    a.G = x->world;
+    a.nq = nq;
+    a.k = k;
+    x->epoch += 1;
+    a.epoch = x->epoch;
+    a.parity = x->epoch & 1;
+    a.slot_bytes = x->slot_bytes;
+    a.flags_off = x->flags_off;
+    a.ids_off = align_up((size_t)nq * k * 4, 16);
+    a.D_loc = D_loc;
+    a.I_loc = I_loc;
+    a.D_out = D_out;
+    a.I_out = I_out;
+    // the grid must be the same on every rank (flags are per block): derived from nq only
+    int blocks = (int)(nq < kExchangeMaxBlocks ? nq : kExchangeMaxBlocks);
+    const size_t smem = (size_t)x->world * k * 12;
+    if (smem > 48 * 1024 && ensure_dynamic_smem(exchange_merge_kernel, 8192 * 12)) return 1;
+    int threads = 512;
+    exchange_merge_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+    KIRAG_LAUNCH_OK("exchange_merge_kernel");
+    return 0;
+}
+
+}  // extern "C"

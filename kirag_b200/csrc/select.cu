@@ -124,97 +124,136 @@ select_pairs_kernel(const Cand* __restrict__ in, int64_t in_stride, const int* _
 // ---- between-level compaction: exact top-m SET + m-th value, no sort -----------
 // After a filter level a query's buffer holds the m kept candidates plus the new survivors
 // (a few thousand at most).  The next level only needs (a) the set of the m best and (b) the
-// m-th best score (the new tau) — not their order.  One CTA per query, items in registers:
-//   1. bits on which all score keys agree are taken from the AND of the keys (no counting);
-//   2. the m-th largest SCORE key is found by a bitwise MSB-first selection over the remaining
-//      bits: one block-wide count and ONE barrier per bit;
+// m-th best score (the new tau) — not their order.  One 256-thread CTA per query (several CTAs
+// per SM), items in registers:
+//   1. bits on which all score keys agree are taken from the AND/OR of the keys (no counting);
+//   2. the m-th largest SCORE key is found by an MSB-first radix selection over the remaining
+//      bits, 8 bits per pass: a 256-bin shared-memory histogram of the still-undecided items,
+//      a suffix scan over the bins, three barriers per pass (scores of one query share their
+//      high bits, so this is 2-4 passes);
 //   3. only if several items tie with that score is the same selection run on the row ids of the
 //      tied items (lower row wins, like the final order);
 //   4. the kept items are compacted back to the front of the list (unordered).
-// A few microseconds instead of a 30-50 us bitonic sort of the whole buffer.
-constexpr int kCompactThreads = 1024;
-constexpr int kCompactPerThread = kSelectSeg / kCompactThreads;  // 8
+constexpr int kCompactThreads = 256;
+constexpr int kCompactWarps = kCompactThreads / 32;
 
-__device__ __forceinline__ int block_sum_1024(int v, int* scratch /* [2][32] */, int parity) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v = __reduce_add_sync(0xffffffffu, v);
-    if (lane == 0) scratch[parity * 32 + warp] = v;
+struct CompactSmem {
+    int hist[2][256];
+    int warp_tot[kCompactWarps];
+    int warp_off[kCompactWarps + 1];
+    unsigned s_and, s_or, s_min;
+    int s_valid;
+    int piv_digit, piv_kk, piv_count;
+};
+
+// Among the items selected by `active(e)`, with digits `digit(e)` in [0, 256): finds the largest
+// digit D such that at least kk active items have a digit >= D.  Returns D; kk becomes the rank
+// still to be resolved INSIDE bin D and n_in_bin the population of bin D.  `hist` must be zero on
+// entry and is left dirty; the caller alternates between the two histograms and re-zeroes the
+// other one meanwhile.
+template <int NS, typename Active, typename Digit>
+__device__ __forceinline__ int radix_pass(CompactSmem& sm, int which, int& kk, int& n_in_bin, Active active,
+                                          Digit digit) {
+    int* hist = sm.hist[which];
+#pragma unroll
+    for (int e = 0; e < NS; ++e)
+        if (active(e)) atomicAdd(&hist[digit(e)], 1);
+    sm.hist[which ^ 1][threadIdx.x] = 0;  // ready for the next pass
     __syncthreads();
-    return __reduce_add_sync(0xffffffffu, scratch[parity * 32 + lane]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = hist[255 - threadIdx.x];  // thread t looks at digit 255 - t: descending digits
+    int incl = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int w = 0; w < kCompactWarps; ++w)
+        if (w < warp) before += sm.warp_tot[w];
+    incl += before;
+    if (incl >= kk && incl - h < kk) {  // exactly one thread: the bin that holds rank kk
+        sm.piv_digit = 255 - threadIdx.x;
+        sm.piv_kk = kk - (incl - h);
+        sm.piv_count = h;
+    }
+    __syncthreads();
+    kk = sm.piv_kk;
+    n_in_bin = sm.piv_count;
+    return sm.piv_digit;
 }
 
-// NS = occupied register slots per thread (compile-time so that the per-bit counting loops carry
-// no dead iterations: the kernel is instruction-issue bound)
+// NS = register slots per thread (compile-time so that the counting loops carry no dead iterations)
 template <int NS>
 __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q, int raw, int count, int cap, int m,
                                                   int* __restrict__ cnt, float* __restrict__ tau,
-                                                  int* __restrict__ overflow, int* scratch, unsigned& s_and,
-                                                  unsigned& s_or, unsigned& s_min, int* warp_off) {
-    constexpr int kCompactPerThread = NS;
-    constexpr int n_slots = NS;
-    uint32_t sk[kCompactPerThread];  // score key, 0 = absent (NaN score / empty slot)
-    uint32_t ik[kCompactPerThread];  // 0xffffffff - row: larger = lower row = better
-    if (threadIdx.x == 0) { s_and = 0xffffffffu; s_or = 0u; }
+                                                  int* __restrict__ overflow, CompactSmem& sm) {
+    uint32_t sk[NS];  // score key, 0 = absent (NaN score / empty slot)
+    uint32_t ik[NS];  // 0xffffffff - row: larger = lower row = better
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { sm.s_and = 0xffffffffu; sm.s_or = 0u; sm.s_valid = 0; sm.s_min = 0xffffffffu; }
+    sm.hist[0][threadIdx.x] = 0;
     int valid_local = 0;
     unsigned my_and = 0xffffffffu, my_or = 0u;
 #pragma unroll
-    for (int e = 0; e < kCompactPerThread; ++e) {
+    for (int e = 0; e < NS; ++e) {
         sk[e] = 0u;
         ik[e] = 0u;
-        if (e < n_slots) {
-            const int i = e * kCompactThreads + threadIdx.x;
-            if (i < count) {
-                const Cand c = list[i];
-                if (c.id >= 0) {
-                    sk[e] = score_key(c.s);
-                    ik[e] = 0xffffffffu - (uint32_t)c.id;
-                }
+        const int i = e * kCompactThreads + threadIdx.x;
+        if (i < count) {
+            const Cand c = list[i];
+            if (c.id >= 0) {
+                sk[e] = score_key(c.s);
+                ik[e] = 0xffffffffu - (uint32_t)c.id;
             }
-            if (sk[e] != 0u) { ++valid_local; my_and &= sk[e]; my_or |= sk[e]; }
         }
+        if (sk[e] != 0u) { ++valid_local; my_and &= sk[e]; my_or |= sk[e]; }
     }
     __syncthreads();
     my_and = __reduce_and_sync(0xffffffffu, my_and);
     my_or = __reduce_or_sync(0xffffffffu, my_or);
-    if ((threadIdx.x & 31) == 0) { atomicAnd(&s_and, my_and); atomicOr(&s_or, my_or); }
-    int parity = 0;
-    const int valid = block_sum_1024(valid_local, scratch, parity);  // its barrier also publishes s_and / s_or
-    parity ^= 1;
+    valid_local = __reduce_add_sync(0xffffffffu, valid_local);
+    if (lane == 0) { atomicAnd(&sm.s_and, my_and); atomicOr(&sm.s_or, my_or); atomicAdd(&sm.s_valid, valid_local); }
+    __syncthreads();
+    const int valid = sm.s_valid;
     const int keep = valid < m ? valid : m;
     uint32_t spiv = 0u, ipiv = 0u;  // keep rule: sk > spiv || (sk == spiv && ik >= ipiv); (0,0) keeps every valid item
     if (valid > m) {
-        const unsigned all_and = s_and, differ = s_and ^ s_or;
+        const unsigned all_and = sm.s_and, differ = sm.s_and ^ sm.s_or;
         int kk = m;
-        uint32_t prefix = all_and & ~differ;  // bits shared by every key are decided already
-        for (int b = 31; b >= 0; --b) {
-            if (!((differ >> b) & 1u)) continue;  // block-uniform
-            const uint32_t cand = (prefix | (1u << b)) >> b;
-            int c_local = 0;
-#pragma unroll
-            for (int e = 0; e < kCompactPerThread; ++e)
-                if (e < n_slots) c_local += (sk[e] != 0u && (sk[e] >> b) == cand);
-            const int c = block_sum_1024(c_local, scratch, parity);
-            parity ^= 1;
-            if (c >= kk) prefix |= (1u << b); else kk -= c;
+        int n_eq = valid;               // items tied with the pivot prefix decided so far
+        int pos = 32 - __clz(differ);   // undecided low bits (0 if every key is the same)
+        uint32_t prefix = (pos >= 32) ? 0u : (all_and >> pos) << pos;  // bits above `pos` are shared by every key
+        int which = 0;
+        while (pos > 0) {
+            const int w = pos < 8 ? pos : 8;
+            const int shift = pos - w;
+            const uint32_t hi = (pos >= 32) ? 0u : (prefix >> pos);
+            const int ppos = pos;
+            const int d = radix_pass<NS>(
+                sm, which, kk, n_eq,
+                [&](int e) { return sk[e] != 0u && ((ppos >= 32) ? 0u : (sk[e] >> ppos)) == hi; },
+                [&](int e) { return (int)((sk[e] >> shift) & ((1u << w) - 1u)); });
+            which ^= 1;
+            prefix |= (uint32_t)d << shift;
+            pos = shift;
         }
-        spiv = prefix;  // score key of the m-th best; kk of the items tied at spiv are kept
-        int eq_local = 0;
-#pragma unroll
-        for (int e = 0; e < kCompactPerThread; ++e)
-            if (e < n_slots) eq_local += (sk[e] == spiv);
-        const int n_eq = block_sum_1024(eq_local, scratch, parity);
-        parity ^= 1;
+        spiv = prefix;  // score key of the m-th best; kk of the n_eq items tied at spiv are kept
         if (n_eq > kk) {  // ties straddle rank m: the kk lowest rows among them win
             uint32_t ipre = 0u;
-            for (int b = 31; b >= 0; --b) {
-                const uint32_t cand = (ipre | (1u << b)) >> b;
-                int c_local = 0;
-#pragma unroll
-                for (int e = 0; e < kCompactPerThread; ++e)
-                    if (e < n_slots) c_local += (sk[e] == spiv && (ik[e] >> b) == cand);
-                const int c = block_sum_1024(c_local, scratch, parity);
-                parity ^= 1;
-                if (c >= kk) ipre |= (1u << b); else kk -= c;
+            int n_in = n_eq;
+            for (int p2 = 32; p2 > 0; p2 -= 8) {
+                const int shift = p2 - 8;
+                const uint32_t hi = (p2 >= 32) ? 0u : (ipre >> p2);
+                const int d = radix_pass<NS>(
+                    sm, which, kk, n_in,
+                    [&](int e) { return sk[e] == spiv && ((p2 >= 32) ? 0u : (ik[e] >> p2)) == hi; },
+                    [&](int e) { return (int)((ik[e] >> shift) & 0xffu); });
+                which ^= 1;
+                ipre |= (uint32_t)d << shift;
             }
             ipiv = ipre;
         }
@@ -222,79 +261,63 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
     // compaction of the kept items back to the front of the list
     int mine = 0;
 #pragma unroll
-    for (int e = 0; e < kCompactPerThread; ++e)
-        if (e < n_slots) mine += (sk[e] != 0u && (sk[e] > spiv || (sk[e] == spiv && ik[e] >= ipiv)));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = 0; e < NS; ++e) mine += (sk[e] != 0u && (sk[e] > spiv || (sk[e] == spiv && ik[e] >= ipiv)));
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) warp_off[warp + 1] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int w = warp_off[lane + 1];
+    if (lane == 31) sm.warp_off[warp + 1] = incl;
+    // the m-th best of exactly m items is their minimum
+    if (valid == m) {
+        uint32_t mn = 0xffffffffu;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
-        }
-        warp_off[lane + 1] = w;
-        if (lane == 0) warp_off[0] = 0;
+        for (int e = 0; e < NS; ++e)
+            if (sk[e] != 0u && sk[e] < mn) mn = sk[e];
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        if (lane == 0) atomicMin(&sm.s_min, mn);
     }
-    __syncthreads();
-    int pos = warp_off[warp] + incl - mine;
+    __syncthreads();  // every read of list[] happened before the loads above: safe to overwrite
+    int pos = incl - mine;
 #pragma unroll
-    for (int e = 0; e < kCompactPerThread; ++e) {
-        if (e < n_slots && sk[e] != 0u && (sk[e] > spiv || (sk[e] == spiv && ik[e] >= ipiv))) {
+    for (int w = 0; w < kCompactWarps; ++w)
+        if (w < warp) pos += sm.warp_off[w + 1];
+#pragma unroll
+    for (int e = 0; e < NS; ++e) {
+        if (sk[e] != 0u && (sk[e] > spiv || (sk[e] == spiv && ik[e] >= ipiv))) {
             Cand c;
             c.s = key_score(sk[e]);
             c.id = (int32_t)(0xffffffffu - ik[e]);
             list[pos++] = c;
         }
     }
-    // new threshold: the m-th best score, once m items exist
-    if (valid > m) {
-        if (threadIdx.x == 0) tau[q] = key_score(spiv);
-    } else if (valid == m) {
-        // nothing dropped; the m-th best is the minimum: smallest key = AND/OR cannot give it, reduce
-        uint32_t mn = 0xffffffffu;
-#pragma unroll
-        for (int e = 0; e < kCompactPerThread; ++e)
-            if (e < n_slots && sk[e] != 0u && sk[e] < mn) mn = sk[e];
-        mn = __reduce_min_sync(0xffffffffu, mn);
-        if (threadIdx.x == 0) s_min = 0xffffffffu;
-        __syncthreads();
-        if (lane == 0) atomicMin(&s_min, mn);
-        __syncthreads();
-        if (threadIdx.x == 0) tau[q] = key_score(s_min);
-    }
     if (threadIdx.x == 0) {
+        // new threshold: the m-th best score, once m items exist
+        if (valid > m) tau[q] = key_score(spiv);
+        else if (valid == m) tau[q] = key_score(sm.s_min);
         cnt[q] = keep;
         if (raw > cap) overflow[q] = 1;
     }
 }
 
-__global__ void __launch_bounds__(kCompactThreads)
+__global__ void __launch_bounds__(kCompactThreads, 4)
 compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cnt, int cap, int m,
                     float* __restrict__ tau, int* __restrict__ overflow) {
-    __shared__ int scratch[64];
-    __shared__ unsigned s_and, s_or, s_min;
-    __shared__ int warp_off[33];
+    __shared__ CompactSmem sm;
     const int q = blockIdx.x;
     const int raw = cnt[q];
     const int count = raw > cap ? cap : raw;
     const int n_slots = (count + kCompactThreads - 1) / kCompactThreads;  // block-uniform
     Cand* list = buf + (int64_t)q * stride;
-#define KIRAG_COMPACT_CASE(NS) \
-    compact_topm_body<NS>(list, q, raw, count, cap, m, cnt, tau, overflow, scratch, s_and, s_or, s_min, warp_off)
-    if (n_slots <= 1) KIRAG_COMPACT_CASE(1);
-    else if (n_slots == 2) KIRAG_COMPACT_CASE(2);
-    else if (n_slots == 3) KIRAG_COMPACT_CASE(3);
-    else if (n_slots == 4) KIRAG_COMPACT_CASE(4);
-    else if (n_slots <= 6) KIRAG_COMPACT_CASE(6);
-    else KIRAG_COMPACT_CASE(8);
+#define KIRAG_COMPACT_CASE(NS) compact_topm_body<NS>(list, q, raw, count, cap, m, cnt, tau, overflow, sm)
+    if (n_slots <= 2) KIRAG_COMPACT_CASE(2);
+    else if (n_slots <= 4) KIRAG_COMPACT_CASE(4);
+    else if (n_slots <= 8) KIRAG_COMPACT_CASE(8);
+    else if (n_slots <= 12) KIRAG_COMPACT_CASE(12);
+    else if (n_slots <= 16) KIRAG_COMPACT_CASE(16);
+    else if (n_slots <= 24) KIRAG_COMPACT_CASE(24);
+    else KIRAG_COMPACT_CASE(32);
 #undef KIRAG_COMPACT_CASE
 }
 

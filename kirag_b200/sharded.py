@@ -4,10 +4,18 @@ No counterpart in the reference (its FAISS search is single-process CPU,
 /root/reference/retriever/index.py:47); this is the multi-GPU form
 BASELINE.json's north_star asks for.  One process per GPU (torchrun).  Rank g
 owns the contiguous global rows [lo_g, hi_g); every rank answers every query
-against its shard with GLOBAL ids (local row + lo_g), one all-gather over
-NCCL/NVLink exchanges the k per-shard candidates per query, and a merge kernel
-takes the global top-k by (score desc, id asc).  Exactness: the global top-k is
-a subset of the union of the per-shard top-k.
+against its shard with GLOBAL ids (local row + lo_g); the k per-shard results
+per query are then exchanged and merged into the global top-k by (score desc,
+id asc).  Exactness: the global top-k is a subset of the union of the per-shard
+top-k.
+
+Two exchanges:
+  "peer" (default on CUDA)  ONE kernel per rank (csrc/exchange.cu) stores its rows
+         into every rank's exchange buffer over NVLink peer memory (CUDA IPC
+         mappings), waits per query range for the peers' rows and merges them;
+  "nccl"  one packed all_gather_into_tensor + kirag_merge_topk (the baseline the
+         peer kernel replaces; also what the gloo CPU tests drive with the
+         oracle plugged in).
 
 The local search and the merge are injectable so that the plumbing (shard
 ranges, id offsets, gather layout) is testable with gloo on CPU, where the
@@ -16,6 +24,7 @@ tests plug the oracle in; the defaults are the CUDA library and nothing else.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -50,12 +59,71 @@ def merge_topk_device(D_all: torch.Tensor, I_all: torch.Tensor) -> Tuple[torch.T
     return D, I
 
 
+class PeerExchange:
+    """This rank's exchange buffer + the IPC mappings of every peer's (kirag_exchange_* C ABI).
+
+    torch.distributed only carries the 64-byte IPC handles at construction time; the data path is
+    the exchange kernel alone.  Every rank must call merge() in the same order with the same
+    shapes (SPMD)."""
+
+    def __init__(self, device: int, rank: int, world_size: int, max_nq: int, max_k: int, group=None):
+        self._lib = _lib.load()
+        self._h = None
+        self.device, self.rank, self.world_size = int(device), int(rank), int(world_size)
+        self.max_nq, self.max_k = int(max_nq), int(max_k)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.kirag_exchange_create(self.device, self.rank, self.world_size, self.max_nq, self.max_k,
+                                                   ctypes.byref(h)), "exchange_create")
+        self._h = h
+        if self.world_size > 1:
+            nb = int(self._lib.kirag_exchange_handle_bytes())
+            mine = ctypes.create_string_buffer(nb)
+            _lib.check(self._lib.kirag_exchange_export(self._h, mine), "exchange_export")
+            handles = [None] * self.world_size
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            blob = b"".join(handles)
+            assert len(blob) == nb * self.world_size
+            _lib.check(self._lib.kirag_exchange_connect(self._h, blob), "exchange_connect")
+            dist.barrier(group=group)  # nobody pushes before every rank has mapped every buffer
+
+    def fits(self, nq: int, k: int) -> bool:
+        return 0 < k <= self.max_k and nq * k <= self.max_nq * self.max_k
+
+    def merge(self, D_loc: torch.Tensor, I_loc: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """D_loc [nq,k] f32, I_loc [nq,k] i64 (this rank's sorted per-shard result) -> global (D, I)."""
+        nq, k = D_loc.shape
+        D_loc = D_loc.contiguous()
+        I_loc = I_loc.contiguous()
+        D = torch.empty_like(D_loc)
+        I = torch.empty_like(I_loc)
+        st = torch.cuda.current_stream(D_loc.device).cuda_stream
+        _lib.check(
+            self._lib.kirag_exchange_merge_topk(self._h, ctypes.c_void_p(D_loc.data_ptr()),
+                                                ctypes.c_void_p(I_loc.data_ptr()), nq, k,
+                                                ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                                ctypes.c_void_p(st)),
+            "exchange_merge_topk")
+        return D, I
+
+    def close(self) -> None:
+        h, self._h = self._h, None
+        if h is not None:
+            self._lib.kirag_exchange_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedFlatIP:
     """SPMD sharded index: every rank calls add_shard()/search() with the same arguments."""
 
     def __init__(self, d: int, n_total: int, rank: Optional[int] = None, world_size: Optional[int] = None,
                  device: Optional[int] = None, group=None,
-                 local_index=None, merge_fn: Optional[Callable] = None):
+                 local_index=None, merge_fn: Optional[Callable] = None, exchange: Optional[str] = None,
+                 max_nq: int = 16384, max_k: int = 128):
         self.d = d
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
@@ -69,6 +137,14 @@ class ShardedFlatIP:
             local_index.reserve(max(self.hi - self.lo, 1))
         self.index = local_index
         self.merge_fn = merge_fn or merge_topk_device
+        # "peer": fused NVLink exchange+merge kernel; "nccl": all-gather + merge kernel.  An injected
+        # local index / merge (the CPU gloo tests) always takes the collective path.
+        injected = merge_fn is not None or not hasattr(self.index, "device")
+        self.exchange = exchange or os.environ.get("KIRAG_EXCHANGE") or ("nccl" if injected else "peer")
+        assert self.exchange in ("peer", "nccl"), f"unknown exchange {self.exchange!r}"
+        self.peer: Optional[PeerExchange] = None
+        if self.exchange == "peer" and self.world_size > 1:
+            self.peer = PeerExchange(self.index.device, self.rank, self.world_size, max_nq, max_k, group=group)
 
     @property
     def ntotal_local(self) -> int:
@@ -92,6 +168,8 @@ class ShardedFlatIP:
         if self.world_size == 1:
             return D_loc, I_loc
         nq = q.shape[0]
+        if self.peer is not None and self.peer.fits(nq, k):
+            return self.peer.merge(D_loc, I_loc)
         # ONE collective for scores and ids: the payload is tiny (12*nq*k bytes per rank), so the
         # exchange is latency-bound and a second all-gather would double its cost.  Scores ride in
         # the same int64 tensor as the ids (bit-cast, zero-extended).
