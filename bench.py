@@ -314,7 +314,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end through the reference-facing call with HOST buffers (rank-local shard; for N > 1 the
-    # all-gather + merge are included through the device path and the final result is copied out)
+    # exchange + merge are included through the device path and the final result is copied out)
     q_host = torch.empty((B, D_MODEL), dtype=torch.float32, pin_memory=True)
     q_host.copy_(q_all[:B].cpu())
     q_np = q_host.numpy()
@@ -367,12 +367,14 @@ def run_ours(args):
                                    f"row-sharded over {world} GPU(s)",
                        "rows": args.rows, "dim": D_MODEL, "batch": B, "k": k, "k_prime": 4 * k,
                        "l2": "inputs (43 GB bf16 shadow) far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"row-shard x{world} + all_gather(k) + merge" if world > 1 else "single GPU"},
+                       "parallelism": (f"row-shard x{world} + " + ("fused NVLink peer-memory exchange+merge kernel"
+                                                                    if sh.peer is not None else "all_gather(k) + merge"))
+                       if world > 1 else "single GPU"},
             "roofline": head["roofline"],
             "cpu_baseline": cpu,
             "e2e": {"value": B / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * D_MODEL * 4, "d2h_bytes_per_step": B * k * 12},
-            "gpu_launches": int(head["stats"].get("kernel_launches", 0)) * args.steps,
+            "gpu_launches": (int(head["stats"].get("kernel_launches", 0)) + (1 if world > 1 else 0)) * args.steps,
             "clocks": clocks,
             "search_stats": head["stats"],
             "sweep": sweep_out,

@@ -272,6 +272,8 @@ static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, 
 }
 
 // ------------------------------------------------------------- fast path ----
+constexpr int kGentleLevels = 1;  // levels after which the walk grows by 4 instead of fp.growth
+
 struct FastParams {
     int kprime;
     int cap;
@@ -290,7 +292,9 @@ static bool fast_eligible(const kirag_index* h, int k, FastParams* fp) {
     int64_t kp = (int64_t)4 * k;  // over-fetch k' = 4k (north_star)
     if (kp < 32) kp = 32;
     if (kp > 2048) return false;
-    int cap = kp <= 128 ? 2048 : 8192;
+    // one buffer size for every k: level 0 is cap/2 rows, so a large buffer also means fewer (latency-bound)
+    // levels on small corpora; 64 KB per query
+    int cap = kSelectSeg;
     cap = env_int("KIRAG_CAND_CAP", cap);
     if (cap > kSelectSeg) cap = kSelectSeg;
     if (cap < 4 * kp) return false;
@@ -374,9 +378,9 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
         prof_mark(30 + levels, st);
         ++levels;
         lo = hi;
-        // the first levels see few distinct tiles, so their tau is a noisy estimate when rows are
-        // clustered by position: grow gently at first
-        const int g = (levels <= 2 && fp.growth > 4) ? 4 : fp.growth;
+        // the first level sees few distinct tiles, so its tau is a noisy estimate when rows are
+        // clustered by position: grow gently at first (16x headroom instead of 4x)
+        const int g = (levels <= kGentleLevels && fp.growth > 4) ? 4 : fp.growth;
         int64_t nh = hi * g;
         hi = (nh > n_tiles) ? n_tiles : nh;
     }
