@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=int(os.environ.get("KIRAG_BENCH_ROWS", 21_000_000)))
     ap.add_argument("--batch", type=int, default=int(os.environ.get("KIRAG_BENCH_BATCH", 4096)))
     ap.add_argument("--k", type=int, default=100)
-    ap.add_argument("--sweep", type=str, default=os.environ.get("KIRAG_BENCH_SWEEP", "1,32,256"),
+    ap.add_argument("--sweep", type=str, default=os.environ.get("KIRAG_BENCH_SWEEP", "1,32,256,1024,16384"),
                     help="extra query batch sizes reported in `sweep` (comma separated, '' for none)")
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the CPU sample (0: 1M for --impl reference, 256k for the cpu_baseline leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -59,6 +59,37 @@ inline int ensure_dynamic_smem(K kernel, size_t bytes) {
     return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
+// ------------------------------------------- programmatic dependent launch ---
+// The kernels of one search form a chain on one stream (init, convert, {scan, compact} per level,
+// rescore, final), many of them a few microseconds long.  They are launched with the
+// programmatic-stream-serialization attribute: a kernel's CTAs may become resident and run their
+// independent prologue (barrier init, TMEM allocation, streaming the first corpus blocks, which no
+// kernel of the chain modifies) while the previous kernel drains; everything that reads data produced
+// earlier in the chain sits behind pdl_wait(), which returns once the previous grid has completed
+// and its memory is visible.  Every kernel triggers its dependents at the very top: the trigger only
+// allows the next grid to be SCHEDULED, ordering comes from pdl_wait() alone.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();  // KIRAG_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------- shadow geometry ---
 constexpr int kTileRows = 128;   // corpus rows per shadow tile (= UMMA M)
 constexpr int kKChunk = 64;      // bf16 elements per 128-byte swizzle row (= one k-block)
@@ -198,7 +229,7 @@ size_t scan_tc_qshadow_bytes(int64_t nq, int d, const ScanTcPlan& plan);
 int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshadow, int64_t nq,
                    const ScanTcPlan& plan, int64_t tile_lo, int64_t tile_hi, int64_t n_tiles,
                    int64_t tile_mult, const float* tau, Cand* cand, int* cnt, int cap, int num_sms,
-                   cudaStream_t st);
+                   int q_dep, cudaStream_t st);
 int launch_scan_tc_dump(const void* shadow, int64_t n_rows, int d, const void* qshadow, int64_t nq,
                         const ScanTcPlan& plan, const float* tau_inf, int* cnt_scratch, float* dump,
                         int64_t dump_ld, int num_sms, cudaStream_t st);

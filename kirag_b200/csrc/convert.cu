@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256)
 convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_t dst_row0,
                     uint8_t* __restrict__ shadow, int rows_per_tile,
                     unsigned* __restrict__ maxnorm2_bits, float* __restrict__ row_norms) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -88,8 +90,8 @@ int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row
     if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride, 16 CTAs per SM
     if (shadow) {
         KIRAG_CHECK(d % 64 == 0, "convert: d=%d is not a multiple of 64", d);
-        convert_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(
-            src, n_rows, d, dst_row0, (uint8_t*)shadow, rows_per_tile, maxnorm2_bits, row_norms);
+        KIRAG_CUDA_OK(launch_chained(convert_rows_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, src, n_rows, d,
+                                     dst_row0, (uint8_t*)shadow, rows_per_tile, maxnorm2_bits, row_norms));
         KIRAG_LAUNCH_OK("convert_rows_kernel");
     } else {
         row_norms_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, n_rows, d, maxnorm2_bits,

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ master, int d, const float* __restrict__ q,
                const Cand* __restrict__ cand, const int* __restrict__ cnt, int cand_stride, int m,
                float* __restrict__ out, int64_t nq, bool vec4) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= nq * m) return;
@@ -44,8 +46,8 @@ int launch_rescore(const float* master, int d, const float* q, const Cand* cand,
     KIRAG_CHECK(blocks < 0x7fffffffLL, "rescore: too many candidates (%lld warps)", (long long)warps);
     const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(master) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
-    rescore_kernel<<<(unsigned)blocks, threads, 0, st>>>(master, d, q, cand, cnt, cand_stride, m,
-                                                        out_scores, nq, vec4);
+    KIRAG_CUDA_OK(launch_chained(rescore_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, master, d, q, cand, cnt,
+                                 cand_stride, m, out_scores, nq, vec4));
     KIRAG_LAUNCH_OK("rescore_kernel");
     return 0;
 }

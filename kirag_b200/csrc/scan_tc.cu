@@ -218,6 +218,8 @@ struct ScanArgs {
     int cap;
     int n_stages;
     int x_policy;      // L2 policy of corpus blocks that are re-read per query tile: 1 normal, 2 evict_last
+    int q_dep;         // 1: the query shadow is written by the kernel right before this one in the chain
+                       // (level 0): the producer must pdl_wait() too; 0: only the filter warps wait
     float* dump;       // optional [n_rows, dump_ld] dense approx scores (debug / tests)
     int64_t dump_ld;
 };
@@ -236,7 +238,7 @@ __device__ __forceinline__ uint32_t pass_mask(const ScanArgs& a, const uint32_t 
     uint32_t pass = 0;
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 t = __ldg(tp + c4);
+        const float4 t = __ldcg(tp + c4);
         pass |= (__uint_as_float(v[c4 * 4 + 0]) >= t.x ? 1u : 0u) << (c4 * 4 + 0);
         pass |= (__uint_as_float(v[c4 * 4 + 1]) >= t.y ? 1u : 0u) << (c4 * 4 + 1);
         pass |= (__uint_as_float(v[c4 * 4 + 2]) >= t.z ? 1u : 0u) << (c4 * 4 + 2);
@@ -293,52 +295,83 @@ __device__ __forceinline__ void stash_store(const ScanArgs& a, const Stash& st) 
     }
 }
 
-// Survivors of one 32-column group.  Deliberately compact, rolled code (it is replicated nowhere and
-// stays out of the instruction cache's way): the surviving columns are re-read one at a time from
-// TMEM (tcgen05.ld x1, dynamic column address) instead of indexing the 32 score registers.
-//   sparse (normal) : every thread parks its few survivors in its Stash
-//   dense (first levels, or a thread would overflow its Stash): lane c owns query column c, one
-//           ballot per surviving column, ONE atomic instruction bumps all counters, then the
-//           columns are stored at the reserved slots
-__device__ __forceinline__ void handle_survivors(const ScanArgs& a, uint32_t taddr_g, uint32_t pass, int64_t q0g,
-                                              int col_g, int32_t row, int lane, Stash& st) {
-    const unsigned uni = __reduce_or_sync(0xffffffffu, pass);
-    const bool dense = __any_sync(0xffffffffu, st.n + __popc(pass) > kStash);
-    if (!dense) {
-        for (unsigned u = uni; u; u &= u - 1) {
-            const int c = __ffs(u) - 1;
-            const uint32_t val = tmem_ld1(taddr_g + c);
-            tmem_ld_wait();
-            if ((pass >> c) & 1u) {
+// 32x32 bit-matrix transpose across the warp: in, lane r holds word A[r] (bit c = A[r][c]); out,
+// lane c holds the word whose bit r is A[r][c].  Five shuffle rounds instead of 32 ballots.
+__device__ __forceinline__ uint32_t warp_transpose_bits(uint32_t x, int lane) {
 #pragma unroll
-                for (int j = 0; j < kStash; ++j)
-                    if (st.n == j) { st.sv[j] = val; st.sc[j] = col_g + c; }
-                ++st.n;
+    for (int s = 0; s < 5; ++s) {
+        const int j = 16 >> s;
+        const uint32_t m = (s == 0) ? 0x0000ffffu : (s == 1) ? 0x00ff00ffu : (s == 2) ? 0x0f0f0f0fu
+                         : (s == 3) ? 0x33333333u : 0x55555555u;
+        const uint32_t t = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((t & ~m) >> j)) : ((x & m) | ((t & m) << j));
+    }
+    return x;
+}
+
+// Survivors of one 32-column group (called only when some lane of the warp has one).  The 32 scores
+// of the group are in registers with STATIC indices; a survivor's column is dynamic, so the scores
+// are first spilled to a 128-byte per-thread scratch (local memory, L1-resident) and then indexed
+// per lane — every lane walks its OWN set bits, the trip count is the largest number of survivors
+// of a single row (1-2 after the first levels), not the number of distinct columns in the warp.
+//   all pass (level 0, tau = -inf): slots are base + row, no ballots or dynamic indexing at all
+//   sparse (normal) : every thread parks its few survivors in its Stash
+//   dense (first levels, or a thread would overflow its Stash): the pass matrix is transposed so
+//           that lane c knows which rows survive query column c; ONE atomic instruction bumps all
+//           32 counters; each row then fetches (base, ballot) of its columns from the owner lanes
+//           by shuffle and stores at base + (number of lower rows that also survive)
+__device__ __forceinline__ void handle_survivors(const ScanArgs& a, const uint32_t (&v)[32], uint32_t pass,
+                                                 int64_t q0g, int col_g, int32_t row, int lane, Stash& st) {
+    if (__all_sync(0xffffffffu, pass == 0xffffffffu)) {
+        // level 0 (tau = -inf): every row survives every column.  Lane c reserves 32 slots of query
+        // column c; row r takes slot base_c + r.  Static register indices, no ballots.
+        int mybase = a.cap;
+        if (q0g + lane < a.nq) mybase = atomicAdd(a.cnt + q0g + lane, 32);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int slot = __shfl_sync(0xffffffffu, mybase, c) + lane;
+            if (slot < a.cap) {
+                Cand cd;
+                cd.s = __uint_as_float(v[c]);
+                cd.id = row;
+                a.cand[(q0g + c) * (int64_t)a.cap + slot] = cd;
             }
         }
         return;
     }
-    unsigned mybal = 0;
-    for (unsigned u = uni; u; u &= u - 1) {
-        const int c = __ffs(u) - 1;
-        const unsigned bal = __ballot_sync(0xffffffffu, (pass >> c) & 1u);
-        if (lane == c) mybal = bal;
+    uint32_t loc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) loc[c] = v[c];
+    const bool dense = __any_sync(0xffffffffu, st.n + __popc(pass) > kStash);
+    if (!dense) {
+        for (uint32_t u = pass; u; u &= u - 1) {
+            const int c = __ffs(u) - 1;
+            const uint32_t val = loc[c];
+#pragma unroll
+            for (int j = 0; j < kStash; ++j)
+                if (st.n == j) { st.sv[j] = val; st.sc[j] = col_g + c; }
+            ++st.n;
+        }
+        return;
     }
+    uint32_t mybal = warp_transpose_bits(pass, lane);  // bit r: row (lane) r survives column `lane`
     if (q0g + lane >= a.nq) mybal = 0;
     int mybase = 0;
     if (mybal != 0) mybase = atomicAdd(a.cnt + q0g + lane, __popc(mybal));
     const unsigned lt = (1u << lane) - 1u;
-    for (unsigned u = uni; u; u &= u - 1) {
-        const int c = __ffs(u) - 1;
+    const int iters = __reduce_max_sync(0xffffffffu, __popc(pass));
+    uint32_t u = pass;
+    for (int i = 0; i < iters; ++i) {
+        const bool has = u != 0;
+        const int c = has ? (__ffs(u) - 1) : 0;
+        u &= u - 1;
         const unsigned bal = __shfl_sync(0xffffffffu, mybal, c);
         const int base = __shfl_sync(0xffffffffu, mybase, c);
-        const uint32_t val = tmem_ld1(taddr_g + c);
-        tmem_ld_wait();
-        if ((bal >> lane) & 1u) {
+        if (has) {
             const int slot = base + __popc(bal & lt);
-            if (slot < a.cap) {
+            if (slot < a.cap && ((bal >> lane) & 1u)) {
                 Cand cd;
-                cd.s = __uint_as_float(val);
+                cd.s = __uint_as_float(loc[c]);
                 cd.id = row;
                 a.cand[(q0g + c) * (int64_t)a.cap + slot] = cd;
             }
@@ -361,7 +394,7 @@ __device__ __forceinline__ void filter_item(const ScanArgs& a, uint32_t taddr, i
         tmem_ld_wait();
         const uint32_t pass = pass_mask(a, v, q0 + g * 32, row, row_ok);
         if (__any_sync(0xffffffffu, pass != 0))
-            handle_survivors(a, taddr + g * 32, pass, q0 + g * 32, g * 32, (int32_t)row, lane, st);
+            handle_survivors(a, v, pass, q0 + g * 32, g * 32, (int32_t)row, lane, st);
     }
     release();
 }
@@ -394,6 +427,9 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
     uint64_t* q_bar = tmem_empty + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(q_bar + 1);
 
+    // HBM-bound variant (idle issue slots): release the dependents at once; the next kernel (compaction)
+    // waits for this whole grid anyway
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = (2 * BQ <= 32) ? 32 : (2 * BQ <= 64) ? 64 : (2 * BQ <= 128) ? 128 : (2 * BQ <= 256) ? 256 : 512;
@@ -421,6 +457,7 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
         if (lane == 0) {
             const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy == 2 ? policy_evict_last() : policy_evict_normal());
             const uint64_t pol_q = policy_evict_last();
+            if (a.q_dep) pdl_wait();  // level 0: the query shadow is being written by the previous kernel
             if (RESIDENT) {
                 mbar_expect_tx(q_bar, (uint32_t)(KC * kQBlockBytes));
                 bulk_g2s(q_res, a.qshadow, (uint32_t)(KC * kQBlockBytes), q_bar, pol_q);
@@ -486,6 +523,7 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
         uint32_t it = 0;
         Stash pend, cur;
         stash_clear(pend);
+        pdl_wait();  // tau / cand / cnt come from the previous compaction; the corpus stream did not have to wait
         for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
             const int64_t tp = w / n_qt;
             const int qt = (int)(w - tp * n_qt);
@@ -581,6 +619,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
         if (lane == 0) {
             const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy == 2 ? policy_evict_last() : policy_evict_normal());
             const uint64_t pol_q = policy_evict_last();
+            if (a.q_dep) pdl_wait();
             int s = 0;
             uint32_t ph = 0;
             for (int64_t w = w_lo; w < w_hi; ++w) {
@@ -655,6 +694,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
         uint32_t it = 0;
         Stash pend, cur;
         stash_clear(pend);
+        pdl_wait();
         for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
             const int64_t p = w / n_qt;
             const int qt = (int)(w - p * n_qt);
@@ -680,6 +720,10 @@ scan_tc_pair_kernel(const ScanArgs a) {
         }
         stash_store(a, pend);
     }
+    // Dependents are released only here: this kernel is tensor/epilogue-bound, and compaction CTAs that
+    // sit resident (blocked in their pdl_wait) next to the filter warps for the whole level measurably
+    // slowed it down; at the end the trigger still hides the next kernel's launch latency.
+    pdl_launch_dependents();
     tc_fence_before();
     cluster_sync_all();  // nobody leaves (or frees TMEM) while the partner can still signal into this CTA
     if (warp == 1) {
@@ -738,7 +782,7 @@ static int launch_scan_pair(const ScanArgs& args_in, int num_sms, cudaStream_t s
     int64_t pairs = ((args.tile_hi - args.tile_lo + 1) / 2) * ((args.nq + kPairQ - 1) / kPairQ);  // work items
     if (pairs > num_sms / 2) pairs = num_sms / 2;
     if (pairs <= 0) return 0;
-    scan_tc_pair_kernel<<<(unsigned)(2 * pairs), EpiCfg<kPairQ>::kThreads, smem, st>>>(args);
+    KIRAG_CUDA_OK(launch_chained(scan_tc_pair_kernel, dim3((unsigned)(2 * pairs)), dim3(EpiCfg<kPairQ>::kThreads), smem, st, args));
     KIRAG_LAUNCH_OK("scan_tc_pair_kernel");
     return 0;
 }
@@ -754,7 +798,7 @@ static int launch_scan_t(const ScanArgs& args_in, int num_sms, cudaStream_t st) 
     int64_t grid = (args.tile_hi - args.tile_lo) * n_qt;  // work items
     if (grid > num_sms) grid = num_sms;
     if (grid <= 0) return 0;
-    scan_tc_kernel<BQ, RESIDENT><<<(unsigned)grid, EpiCfg<BQ>::kThreads, smem, st>>>(args);
+    KIRAG_CUDA_OK(launch_chained(scan_tc_kernel<BQ, RESIDENT>, dim3((unsigned)grid), dim3(EpiCfg<BQ>::kThreads), smem, st, args));
     KIRAG_LAUNCH_OK("scan_tc_kernel");
     return 0;
 }
@@ -772,8 +816,9 @@ static int launch_scan_args(const ScanArgs& args, const ScanTcPlan& plan, int nu
 int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshadow, int64_t nq,
                    const ScanTcPlan& plan, int64_t tile_lo, int64_t tile_hi, int64_t n_tiles,
                    int64_t tile_mult, const float* tau, Cand* cand, int* cnt, int cap, int num_sms,
-                   cudaStream_t st) {
+                   int q_dep, cudaStream_t st) {
     ScanArgs args{};
+    args.q_dep = q_dep;
     args.shadow = (const uint8_t*)shadow;
     args.qshadow = (const uint8_t*)qshadow;
     args.n_rows = n_rows;
@@ -812,6 +857,7 @@ int launch_scan_tc_dump(const void* shadow, int64_t n_rows, int d, const void* q
     args.cap = 0;
     args.dump = dump;
     args.dump_ld = dump_ld;
+    args.q_dep = 1;
     return launch_scan_args(args, plan, num_sms, st);
 }
 

@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(kCompactThreads, 4)
 compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cnt, int cap, int m,
                     float* __restrict__ tau, int* __restrict__ overflow) {
     __shared__ CompactSmem sm;
+    pdl_wait();
+    pdl_launch_dependents();
     const int q = blockIdx.x;
     const int raw = cnt[q];
     const int count = raw > cap ? cap : raw;
@@ -336,6 +338,8 @@ final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __
              const int* __restrict__ overflow, int* __restrict__ flags,
              const int* __restrict__ qmap) {
     extern __shared__ uint64_t items[];
+    pdl_wait();
+    pdl_launch_dependents();
     const int q = blockIdx.x;
     int count = cnt ? cnt[q] : fixed_count;
     if (count > m_in) count = m_in;
@@ -364,8 +368,8 @@ final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __
         I[qo * k + j] = id;
     }
     if (threadIdx.x == 0 && flags) {
-        int fail = 0;
-        if (overflow && overflow[q]) fail = 1;
+        int fail = 0;  // 0 ok, 1 certificate failed, 2 candidate buffer overflowed
+        const bool ovf = overflow && overflow[q];
         if (check_cert && tau) {
             const float t = tau[q];
             if (t > -INFINITY) {
@@ -380,7 +384,7 @@ final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __
                 }
             }
         }
-        flags[q] = fail;
+        flags[q] = ovf ? 2 : fail;
     }
 }
 
@@ -500,7 +504,8 @@ int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, in
                         cudaStream_t st) {
     KIRAG_CHECK(cap <= kSelectSeg && m <= cap, "compact_topm: cap=%d m=%d out of range", cap, m);
     if (nq <= 0) return 0;
-    compact_topm_kernel<<<(unsigned)nq, kCompactThreads, 0, st>>>(buf, stride, cnt, cap, m, tau, overflow);
+    KIRAG_CUDA_OK(launch_chained(compact_topm_kernel, dim3((unsigned)nq), dim3(kCompactThreads), 0, st, buf, stride, cnt,
+                                 cap, m, tau, overflow));
     KIRAG_LAUNCH_OK("compact_topm_kernel");
     return 0;
 }
@@ -513,9 +518,9 @@ int launch_final(const Cand* cand, int64_t cand_stride, const float* rescored, c
     const int P = host_pow2(m_in);
     const size_t smem = (size_t)P * 8;
     if (ensure_smem(final_kernel, (size_t)kSelectSeg * 8)) return 1;
-    final_kernel<<<(unsigned)nq, sort_threads(P), smem, st>>>(
-        cand, cand_stride, rescored, cnt, fixed_count, m_in, k, D, I, id_offset, tau, qnorm,
-        eps_factor, check_cert, overflow, flags, qmap);
+    KIRAG_CUDA_OK(launch_chained(final_kernel, dim3((unsigned)nq), dim3(sort_threads(P)), smem, st, cand, cand_stride,
+                                 rescored, cnt, fixed_count, m_in, k, D, I, id_offset, tau, qnorm, eps_factor, check_cert,
+                                 overflow, flags, qmap));
     KIRAG_LAUNCH_OK("final_kernel");
     return 0;
 }
