@@ -290,12 +290,22 @@ static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, 
 }
 
 // ------------------------------------------------------------- fast path ----
-constexpr int kGentleLevels = 1;  // levels after which the walk grows by 4 instead of fp.growth
+// Level schedule of the filter path (tiles of 128 rows, walked in a pseudo-random order):
+//   level 0   cap/2 rows, everything is appended (tau = -inf)
+//   level 1   grows the prefix 4x: tau comes from few distinct tiles and is a noisy estimate when rows
+//             are clustered by position, so the first step keeps 16x headroom in the buffer
+//   then      L equal geometric steps with growth g <= g_max = cap / (4 k') (expected survivors of a
+//             level = k' * g, 4x headroom), L the smallest count that reaches the end: equal steps
+//             append the fewest survivors in total for a given number of launches
+// Small query batches (<= kWideCapMaxQueries) get a 4x larger candidate buffer: the filter has slack
+// there (HBM-bound), launches are what costs, and a 4x larger g_max removes two to three levels.
+constexpr int64_t kWideCapMaxQueries = 64;
+constexpr int kMaxGrowth = 32;
 
 struct FastParams {
     int kprime;
-    int cap;
-    int growth;
+    int growth_override;  // KIRAG_LEVEL_GROWTH (0: automatic)
+    int cap_override;     // KIRAG_CAND_CAP (0: automatic)
 };
 
 static int env_int(const char* name, int dflt) {
@@ -310,22 +320,49 @@ static bool fast_eligible(const kirag_index* h, int k, FastParams* fp) {
     int64_t kp = (int64_t)4 * k;  // over-fetch k' = 4k (north_star)
     if (kp < 32) kp = 32;
     if (kp > 2048) return false;
-    // one buffer size for every k: level 0 is cap/2 rows, so a large buffer also means fewer (latency-bound)
-    // levels on small corpora; 64 KB per query
-    int cap = kSelectSeg;
-    cap = env_int("KIRAG_CAND_CAP", cap);
-    if (cap > kSelectSeg) cap = kSelectSeg;
-    if (cap < 4 * kp) return false;
-    // expected survivors of a level = k' * growth (incl. the k' kept); keep 4x headroom in the buffer
-    int growth = (int)(cap / (4 * kp));
-    if (growth > 16) growth = 16;
-    if (growth < 2) growth = 2;
-    growth = env_int("KIRAG_LEVEL_GROWTH", growth);
-    if (growth < 2) growth = 2;
     fp->kprime = (int)kp;
-    fp->cap = cap;
-    fp->growth = growth;
+    fp->growth_override = env_int("KIRAG_LEVEL_GROWTH", 0);
+    fp->cap_override = env_int("KIRAG_CAND_CAP", 0);
+    if (fp->cap_override > 0 && fp->cap_override < 4 * kp) return false;
     return true;
+}
+
+static int pick_cap(const FastParams& fp, int64_t nq) {
+    int cap = (nq <= kWideCapMaxQueries) ? kWideCap : kSelectSeg;
+    if (fp.cap_override > 0) cap = fp.cap_override;
+    if (cap > kWideCap) cap = kWideCap;
+    return cap;
+}
+
+// upper tile bound (exclusive) of every level
+static std::vector<int64_t> level_bounds(int64_t n_tiles, int cap, const FastParams& fp) {
+    std::vector<int64_t> hi;
+    int64_t t = (cap / 2) / kTileRows;
+    if (t < 1) t = 1;
+    if (t > n_tiles) t = n_tiles;
+    hi.push_back(t);
+    if (t >= n_tiles) return hi;
+    int gmax = cap / (4 * fp.kprime);
+    if (gmax > kMaxGrowth) gmax = kMaxGrowth;
+    if (fp.growth_override > 0) gmax = fp.growth_override;
+    if (gmax < 2) gmax = 2;
+    t = t * (gmax < 4 ? gmax : 4);
+    if (t > n_tiles) t = n_tiles;
+    hi.push_back(t);
+    if (t >= n_tiles) return hi;
+    const double ratio = (double)n_tiles / (double)t;
+    int L = (int)ceil(log(ratio) / log((double)gmax) - 1e-9);
+    if (L < 1) L = 1;
+    const double g = pow(ratio, 1.0 / L);
+    const int64_t base = t;
+    for (int i = 1; i <= L; ++i) {
+        int64_t b = (i == L) ? n_tiles : (int64_t)ceil((double)base * pow(g, (double)i));
+        if (b <= hi.back()) b = hi.back() + 1;
+        if (b > n_tiles) b = n_tiles;
+        hi.push_back(b);
+        if (b >= n_tiles) break;
+    }
+    return hi;
 }
 
 static int64_t pick_tile_mult(int64_t n_tiles) {
@@ -354,7 +391,8 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
     if (h->qshadow.ensure(qs_bytes)) return 1;
     if (h->qnorm.ensure((size_t)nq * 4)) return 1;
-    if (h->cand.ensure((size_t)nq * fp.cap * sizeof(Cand))) return 1;
+    const int cap = pick_cap(fp, nq);
+    if (h->cand.ensure((size_t)nq * cap * sizeof(Cand))) return 1;
     if (h->cnt.ensure((size_t)nq * 4)) return 1;
     const int64_t nq_pad = round_up(nq, 256);
     if (h->tau.ensure((size_t)nq_pad * 4)) return 1;
@@ -372,12 +410,10 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
 
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
     const int64_t mult = pick_tile_mult(n_tiles);
+    const std::vector<int64_t> bounds = level_bounds(n_tiles, cap, fp);
     int64_t lo = 0;
-    int64_t hi = (fp.cap / 2) / kTileRows;
-    if (hi < 1) hi = 1;
-    if (hi > n_tiles) hi = n_tiles;
     int levels = 0;
-    while (lo < n_tiles) {
+    for (const int64_t hi : bounds) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (g_prof.on) {
             KIRAG_CUDA_OK(cudaEventCreate(&e0));
@@ -385,7 +421,7 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
             KIRAG_CUDA_OK(cudaEventRecord(e0, st));
         }
         if (launch_scan_tc(h->shadow, n, d, h->qshadow.p, nq, plan, lo, hi, n_tiles, mult,
-                           h->tau.as<float>(), h->cand.as<Cand>(), h->cnt.as<int>(), fp.cap, h->num_sms,
+                           h->tau.as<float>(), h->cand.as<Cand>(), h->cnt.as<int>(), cap, h->num_sms,
                            levels == 0 ? 1 : 0, st)) return 1;
         if (g_prof.on) {
             KIRAG_CUDA_OK(cudaEventRecord(e1, st));
@@ -396,24 +432,19 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
             g_prof.queries = (double)nq;
         }
         prof_mark(10 + levels, st);
-        if (launch_compact_topm(h->cand.as<Cand>(), fp.cap, h->cnt.as<int>(), fp.cap, (int)nq, fp.kprime,
+        if (launch_compact_topm(h->cand.as<Cand>(), cap, h->cnt.as<int>(), cap, (int)nq, fp.kprime,
                                 h->tau.as<float>(), h->overflow.as<int>(), st)) return 1;
         prof_mark(30 + levels, st);
         ++levels;
         lo = hi;
-        // the first level sees few distinct tiles, so its tau is a noisy estimate when rows are
-        // clustered by position: grow gently at first (16x headroom instead of 4x)
-        const int g = (levels <= kGentleLevels && fp.growth > 4) ? 4 : fp.growth;
-        int64_t nh = hi * g;
-        hi = (nh > n_tiles) ? n_tiles : nh;
     }
-    if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), fp.cap, fp.kprime,
+    if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), cap, fp.kprime,
                        h->rescored.as<float>(), nq, st)) return 1;
     prof_mark(50, st);
     // eps bounds |approx - canonical|: bf16 rounding of both operands (2 * 2^-9, plus
     // the cross term) and fp32 accumulation slack, times ||q|| * max_j ||x_j||
     const float eps_factor = (float)((ldexp(1.0, -8) * 1.002 + (double)d * ldexp(1.0, -21)) * (double)h->maxnorm);
-    if (launch_final(h->cand.as<Cand>(), fp.cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, fp.kprime,
+    if (launch_final(h->cand.as<Cand>(), cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, fp.kprime,
                      (int)nq, k, D, I, id_offset, h->tau.as<float>(), h->qnorm.as<float>(), eps_factor,
                      check_cert, h->overflow.as<int>(), h->flags.as<int>(), nullptr, st)) return 1;
     prof_mark(51, st);

@@ -202,6 +202,7 @@ int launch_rescore(const float* master, int d, const float* q, const Cand* cand,
                    int cand_stride, int m, float* out_scores, int64_t nq, cudaStream_t st);
 // select.cu
 constexpr int kSelectSeg = 8192;
+constexpr int kWideCap = 32768;  // candidate buffer of small query batches (fewer, longer levels)
 int launch_select_dense(const float* scores, int64_t ld, int64_t n, int nq, int m, Cand* out,
                         int* n_seg_out, cudaStream_t st);
 int launch_select_pairs(const Cand* in, int64_t in_stride, const int* cnt, int fixed_count, int cap,

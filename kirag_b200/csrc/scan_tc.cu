@@ -218,6 +218,7 @@ struct ScanArgs {
     int cap;
     int n_stages;
     int x_policy;      // L2 policy of corpus blocks that are re-read per query tile: 1 normal, 2 evict_last
+    int tau_ldg;       // experiment switch (KIRAG_TAU_LDG=1): read tau through L1 instead of L2
     int q_dep;         // 1: the query shadow is written by the kernel right before this one in the chain
                        // (level 0): the producer must pdl_wait() too; 0: only the filter warps wait
     float* dump;       // optional [n_rows, dump_ld] dense approx scores (debug / tests)
@@ -232,17 +233,31 @@ struct ScanArgs {
 // counters of ALL groups are bumped by NG independent atomic instructions (one round trip in
 // total, not one per group), and pass 2 re-reads from TMEM only the groups that have survivors
 // and stores (score, row) at the reserved slots.
+// TAU_SHFL: the thresholds of this warp's columns live in registers (lane l holds tau of column
+// g*32 + l, loaded once per query tile through L2) and are broadcast by shuffles.  Otherwise they are
+// read per group with vector loads through L2.  tau must not be read through L1 / the non-coherent
+// path: it is rewritten by the previous kernel of a programmatically chained launch, and an L2 load in
+// the loop costs the HBM-bound variants 16% (the accumulator is held while the load is in flight).
+template <bool TAU_SHFL>
 __device__ __forceinline__ uint32_t pass_mask(const ScanArgs& a, const uint32_t (&v)[32], int64_t q0, int64_t row,
-                                              bool row_ok) {
-    const float4* tp = reinterpret_cast<const float4*>(a.tau + q0);
+                                              bool row_ok, float mytau) {
     uint32_t pass = 0;
+    if (TAU_SHFL) {
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 t = __ldcg(tp + c4);
-        pass |= (__uint_as_float(v[c4 * 4 + 0]) >= t.x ? 1u : 0u) << (c4 * 4 + 0);
-        pass |= (__uint_as_float(v[c4 * 4 + 1]) >= t.y ? 1u : 0u) << (c4 * 4 + 1);
-        pass |= (__uint_as_float(v[c4 * 4 + 2]) >= t.z ? 1u : 0u) << (c4 * 4 + 2);
-        pass |= (__uint_as_float(v[c4 * 4 + 3]) >= t.w ? 1u : 0u) << (c4 * 4 + 3);
+        for (int c = 0; c < 32; ++c) {
+            const float t = __shfl_sync(0xffffffffu, mytau, c);
+            pass |= (__uint_as_float(v[c]) >= t ? 1u : 0u) << c;
+        }
+    } else {
+        const float4* tp = reinterpret_cast<const float4*>(a.tau + q0);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 t = a.tau_ldg ? __ldg(tp + c4) : __ldcg(tp + c4);
+            pass |= (__uint_as_float(v[c4 * 4 + 0]) >= t.x ? 1u : 0u) << (c4 * 4 + 0);
+            pass |= (__uint_as_float(v[c4 * 4 + 1]) >= t.y ? 1u : 0u) << (c4 * 4 + 1);
+            pass |= (__uint_as_float(v[c4 * 4 + 2]) >= t.z ? 1u : 0u) << (c4 * 4 + 2);
+            pass |= (__uint_as_float(v[c4 * 4 + 3]) >= t.w ? 1u : 0u) << (c4 * 4 + 3);
+        }
     }
     if (!row_ok) pass = 0;
     if (a.dump && row_ok) {
@@ -381,9 +396,9 @@ __device__ __forceinline__ void handle_survivors(const ScanArgs& a, const uint32
 
 // taddr: TMEM address of this warp's first column (lane quadrant included); q0: first query of it.
 // `release` is called exactly once, right after this warp's last read of the accumulator.
-template <int NG, typename Release>
+template <int NG, bool TAU_SHFL, typename Release>
 __device__ __forceinline__ void filter_item(const ScanArgs& a, uint32_t taddr, int64_t q0, int64_t row, bool row_ok,
-                                            int lane, Stash& st, Release release) {
+                                            int lane, Stash& st, const float (&mytau)[NG], Release release) {
     stash_clear(st);
     st.q0 = q0;
     st.row = (int32_t)row;
@@ -392,7 +407,7 @@ __device__ __forceinline__ void filter_item(const ScanArgs& a, uint32_t taddr, i
         uint32_t v[32];
         tmem_ld32(taddr + g * 32, v);
         tmem_ld_wait();
-        const uint32_t pass = pass_mask(a, v, q0 + g * 32, row, row_ok);
+        const uint32_t pass = pass_mask<TAU_SHFL>(a, v, q0 + g * 32, row, row_ok, mytau[g]);
         if (__any_sync(0xffffffffu, pass != 0))
             handle_survivors(a, v, pass, q0 + g * 32, g * 32, (int32_t)row, lane, st);
     }
@@ -524,6 +539,8 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
         Stash pend, cur;
         stash_clear(pend);
         pdl_wait();  // tau / cand / cnt come from the previous compaction; the corpus stream did not have to wait
+        float mytau[NG];
+        int tau_qt = -1;
         for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
             const int64_t tp = w / n_qt;
             const int qt = (int)(w - tp * n_qt);
@@ -532,11 +549,16 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
             const bool row_ok = row < a.n_rows;
             const uint32_t as = it & 1u;
             const uint32_t aph = (it >> 1) & 1u;
+            if (qt != tau_qt) {  // once per launch when the batch is a single query tile; in flight during the wait below
+#pragma unroll
+                for (int g = 0; g < NG; ++g) mytau[g] = __ldcg(a.tau + (int64_t)qt * BQ + col0 + g * 32 + lane);
+                tau_qt = qt;
+            }
             mbar_wait(&tmem_full[as], aph, 500 + as);
             tc_fence_after();
             uint64_t* const ebar = &tmem_empty[as];
-            filter_item<NG>(a, tmem_base + lane_base + as * BQ + col0, (int64_t)qt * BQ + col0, row, row_ok, lane,
-                            cur, [=]() {
+            filter_item<NG, true>(a, tmem_base + lane_base + as * BQ + col0, (int64_t)qt * BQ + col0, row, row_ok, lane,
+                            cur, mytau, [=]() {
                                 // all of this warp's reads of the accumulator are done
                                 tc_fence_before();
                                 __syncwarp();
@@ -695,6 +717,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
         Stash pend, cur;
         stash_clear(pend);
         pdl_wait();
+        const float no_tau[NG] = {};
         for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
             const int64_t p = w / n_qt;
             const int qt = (int)(w - p * n_qt);
@@ -708,8 +731,8 @@ scan_tc_pair_kernel(const ScanArgs a) {
             mbar_wait(&tmem_full[as], aph, 500 + as);
             tc_fence_after();
             const uint32_t ebar = leader_empty[as];
-            filter_item<NG>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
-                            lane, cur, [=]() {
+            filter_item<NG, false>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
+                            lane, cur, no_tau, [=]() {
                                 tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_cluster(ebar);
@@ -819,6 +842,7 @@ int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshado
                    int q_dep, cudaStream_t st) {
     ScanArgs args{};
     args.q_dep = q_dep;
+    args.tau_ldg = env_flag("KIRAG_TAU_LDG", 0);
     args.shadow = (const uint8_t*)shadow;
     args.qshadow = (const uint8_t*)qshadow;
     args.n_rows = n_rows;

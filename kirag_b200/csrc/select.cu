@@ -134,13 +134,14 @@ select_pairs_kernel(const Cand* __restrict__ in, int64_t in_stride, const int* _
 //   3. only if several items tie with that score is the same selection run on the row ids of the
 //      tied items (lower row wins, like the final order);
 //   4. the kept items are compacted back to the front of the list (unordered).
-constexpr int kCompactThreads = 256;
-constexpr int kCompactWarps = kCompactThreads / 32;
+constexpr int kCompactThreads = 256;       // normal buffers (<= kSelectSeg items): several CTAs per SM
+constexpr int kCompactThreadsWide = 1024;  // wide buffers of small query batches (<= kWideCap items)
+constexpr int kCompactMaxWarps = kCompactThreadsWide / 32;
 
 struct CompactSmem {
     int hist[2][256];
-    int warp_tot[kCompactWarps];
-    int warp_off[kCompactWarps + 1];
+    int warp_tot[8];                       // the bin scan is always done by the first 256 threads
+    int warp_off[kCompactMaxWarps + 1];
     unsigned s_and, s_or, s_min;
     int s_valid;
     int piv_digit, piv_kk, piv_count;
@@ -158,27 +159,33 @@ __device__ __forceinline__ int radix_pass(CompactSmem& sm, int which, int& kk, i
 #pragma unroll
     for (int e = 0; e < NS; ++e)
         if (active(e)) atomicAdd(&hist[digit(e)], 1);
-    sm.hist[which ^ 1][threadIdx.x] = 0;  // ready for the next pass
+    const bool binner = threadIdx.x < 256;  // warp-uniform: whole warps 0..7
+    if (binner) sm.hist[which ^ 1][threadIdx.x] = 0;  // ready for the next pass
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int h = hist[255 - threadIdx.x];  // thread t looks at digit 255 - t: descending digits
-    int incl = h;
+    int h = 0, incl = 0;
+    if (binner) {
+        h = hist[255 - threadIdx.x];  // thread t looks at digit 255 - t: descending digits
+        incl = h;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sm.warp_tot[warp] = incl;
     }
-    if (lane == 31) sm.warp_tot[warp] = incl;
     __syncthreads();
-    int before = 0;
+    if (binner) {
+        int before = 0;
 #pragma unroll
-    for (int w = 0; w < kCompactWarps; ++w)
-        if (w < warp) before += sm.warp_tot[w];
-    incl += before;
-    if (incl >= kk && incl - h < kk) {  // exactly one thread: the bin that holds rank kk
-        sm.piv_digit = 255 - threadIdx.x;
-        sm.piv_kk = kk - (incl - h);
-        sm.piv_count = h;
+        for (int w = 0; w < 8; ++w)
+            if (w < warp) before += sm.warp_tot[w];
+        incl += before;
+        if (incl >= kk && incl - h < kk) {  // exactly one thread: the bin that holds rank kk
+            sm.piv_digit = 255 - threadIdx.x;
+            sm.piv_kk = kk - (incl - h);
+            sm.piv_count = h;
+        }
     }
     __syncthreads();
     kk = sm.piv_kk;
@@ -187,7 +194,7 @@ __device__ __forceinline__ int radix_pass(CompactSmem& sm, int which, int& kk, i
 }
 
 // NS = register slots per thread (compile-time so that the counting loops carry no dead iterations)
-template <int NS>
+template <int NS, int THREADS>
 __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q, int raw, int count, int cap, int m,
                                                   int* __restrict__ cnt, float* __restrict__ tau,
                                                   int* __restrict__ overflow, CompactSmem& sm) {
@@ -195,14 +202,14 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
     uint32_t ik[NS];  // 0xffffffff - row: larger = lower row = better
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { sm.s_and = 0xffffffffu; sm.s_or = 0u; sm.s_valid = 0; sm.s_min = 0xffffffffu; }
-    sm.hist[0][threadIdx.x] = 0;
+    if (threadIdx.x < 256) sm.hist[0][threadIdx.x] = 0;
     int valid_local = 0;
     unsigned my_and = 0xffffffffu, my_or = 0u;
 #pragma unroll
     for (int e = 0; e < NS; ++e) {
         sk[e] = 0u;
         ik[e] = 0u;
-        const int i = e * kCompactThreads + threadIdx.x;
+        const int i = e * THREADS + threadIdx.x;
         if (i < count) {
             const Cand c = list[i];
             if (c.id >= 0) {
@@ -281,7 +288,7 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
     __syncthreads();  // every read of list[] happened before the loads above: safe to overwrite
     int pos = incl - mine;
 #pragma unroll
-    for (int w = 0; w < kCompactWarps; ++w)
+    for (int w = 0; w < THREADS / 32; ++w)
         if (w < warp) pos += sm.warp_off[w + 1];
 #pragma unroll
     for (int e = 0; e < NS; ++e) {
@@ -301,7 +308,8 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
     }
 }
 
-__global__ void __launch_bounds__(kCompactThreads, 4)
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cnt, int cap, int m,
                     float* __restrict__ tau, int* __restrict__ overflow) {
     __shared__ CompactSmem sm;
@@ -310,9 +318,9 @@ compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cn
     const int q = blockIdx.x;
     const int raw = cnt[q];
     const int count = raw > cap ? cap : raw;
-    const int n_slots = (count + kCompactThreads - 1) / kCompactThreads;  // block-uniform
+    const int n_slots = (count + THREADS - 1) / THREADS;  // block-uniform
     Cand* list = buf + (int64_t)q * stride;
-#define KIRAG_COMPACT_CASE(NS) compact_topm_body<NS>(list, q, raw, count, cap, m, cnt, tau, overflow, sm)
+#define KIRAG_COMPACT_CASE(NS) compact_topm_body<NS, THREADS>(list, q, raw, count, cap, m, cnt, tau, overflow, sm)
     if (n_slots <= 2) KIRAG_COMPACT_CASE(2);
     else if (n_slots <= 4) KIRAG_COMPACT_CASE(4);
     else if (n_slots <= 8) KIRAG_COMPACT_CASE(8);
@@ -502,10 +510,15 @@ int launch_select_pairs(const Cand* in, int64_t in_stride, const int* cnt, int f
 
 int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, int m, float* tau, int* overflow,
                         cudaStream_t st) {
-    KIRAG_CHECK(cap <= kSelectSeg && m <= cap, "compact_topm: cap=%d m=%d out of range", cap, m);
+    KIRAG_CHECK(cap <= kWideCap && m <= cap, "compact_topm: cap=%d m=%d out of range", cap, m);
     if (nq <= 0) return 0;
-    KIRAG_CUDA_OK(launch_chained(compact_topm_kernel, dim3((unsigned)nq), dim3(kCompactThreads), 0, st, buf, stride, cnt,
-                                 cap, m, tau, overflow));
+    if (cap <= kSelectSeg) {
+        KIRAG_CUDA_OK(launch_chained(compact_topm_kernel<kCompactThreads, 4>, dim3((unsigned)nq), dim3(kCompactThreads), 0,
+                                     st, buf, stride, cnt, cap, m, tau, overflow));
+    } else {
+        KIRAG_CUDA_OK(launch_chained(compact_topm_kernel<kCompactThreadsWide, 1>, dim3((unsigned)nq),
+                                     dim3(kCompactThreadsWide), 0, st, buf, stride, cnt, cap, m, tau, overflow));
+    }
     KIRAG_LAUNCH_OK("compact_topm_kernel");
     return 0;
 }
