@@ -266,7 +266,8 @@ def measure_batch(sh, lib, q_all, batch, k, steps, warmup, device, dist_ok, peak
     if world == 1 and rows_total == 21_000_000 and k == 100 and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(str(batch), {}).get("dram_bytes_per_step")
     roof.update({"traffic": traffic, "traffic_note": "bytes per step (all scan launches of one step), ncu capture",
-                 "kernel": "scan_tc_pair_kernel" if batch > 128 else "scan_tc_kernel", "kernel_ms_per_step": scan_ms_step,
+                 "kernel": ("scan_tc_pair_kernel<256,streamed>" if batch > 128 else "scan_tc_pair_kernel<128,resident>"
+                            if batch > 64 else "scan_tc_kernel<%d,resident>" % (32 if batch <= 32 else 64)), "kernel_ms_per_step": scan_ms_step,
                  "kernel_share_of_step": scan_ms_step / ms if ms > 0 else None,
                  "launches_per_step": launches.value / steps, "peak_source": peaks["source"],
                  "algorithmic_bytes_per_step": bytes_alg, "algorithmic_flops_per_step": flops_alg,

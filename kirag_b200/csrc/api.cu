@@ -299,7 +299,7 @@ static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, 
 //             append the fewest survivors in total for a given number of launches
 // Small query batches (<= kWideCapMaxQueries) get a 4x larger candidate buffer: the filter has slack
 // there (HBM-bound), launches are what costs, and a 4x larger g_max removes two to three levels.
-constexpr int64_t kWideCapMaxQueries = 64;
+constexpr int64_t kWideCapMaxQueries = 128;
 constexpr int kMaxGrowth = 32;
 
 struct FastParams {
@@ -830,11 +830,15 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
     if (scan_tc_pick(nq, d, &plan)) return 1;
     const char* force = getenv("KIRAG_DEBUG_BQ");
     if (force && *force) {
+        // 32 / 64 / 128 / 256: single-CTA kernels (32 resident, the others streamed); 512: the 2-CTA kernel
+        // with 256-query tiles; 1128: the 2-CTA kernel with a resident 128-query tile; 1064: resident 64
         plan.bq = atoi(force);
         plan.pair = 0;
-        if (plan.bq == 512) { plan.bq = 256; plan.pair = 1; }  // KIRAG_DEBUG_BQ=512 selects the 2-CTA kernel
         plan.resident = (plan.bq == 32) ? 1 : 0;
-        plan.q_tile_rows = plan.pair ? 128 : plan.bq;
+        if (plan.bq == 512) { plan.bq = 256; plan.pair = 1; }
+        if (plan.bq == 1128) { plan.bq = 128; plan.pair = 1; plan.resident = 1; }
+        if (plan.bq == 1064) { plan.bq = 64; plan.resident = 1; }
+        plan.q_tile_rows = plan.pair ? plan.bq / 2 : plan.bq;
     }
     const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
     const int64_t nq_pad = round_up(nq, 256);

@@ -590,30 +590,44 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
 // Barriers: full[s] lives in each CTA (leader: own expect_tx + the peer's forwarded arrive);
 // empty[s] and tmem_full[a] are signalled in both CTAs by a multicast tcgen05.commit;
 // tmem_empty[a] of the LEADER collects the 8 filter warps of both CTAs.
-constexpr int kPairQ = 256;       // queries per work item (UMMA N)
-constexpr int kPairHalfQ = 128;   // query rows staged per CTA
-constexpr int kPairStageBytes = kBlockBytes + kPairHalfQ * 128;  // 32 KB
+// Two instantiations:
+//   PQ = 256, streamed  : large batches (tensor-bound); corpus block + half query block per stage
+//   PQ = 128, RES       : 64 < batch <= 128 (HBM-bound); each CTA keeps ITS half of the single query
+//                         tile (64 queries x d, 128 KB at d = 1024) resident in shared memory, so
+//                         only corpus blocks are streamed: L2 -> SM traffic equals the HBM traffic
+template <int PQ, bool RES> struct PairCfg {
+    static constexpr int kHalfQ = PQ / 2;                      // query rows staged per CTA
+    static constexpr int kQHalfBytes = kHalfQ * 128;           // one [half x 64] bf16 block
+    static constexpr int kStageBytes = kBlockBytes + (RES ? 0 : kQHalfBytes);
+};
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<kPairQ>::kThreads, 1)
+template <int PQ, bool RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<PQ>::kThreads, 1)
 scan_tc_pair_kernel(const ScanArgs a) {
+    constexpr int kPairQ = PQ;
+    constexpr int kPairHalfQ = PairCfg<PQ, RES>::kHalfQ;
+    constexpr int kQHalfBytes = PairCfg<PQ, RES>::kQHalfBytes;
+    constexpr int kPairStageBytes = PairCfg<PQ, RES>::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int KC = a.d >> 6;
     const int NS = a.n_stages;
     uint8_t* stage_base = smem;
-    uint8_t* tail = smem + (size_t)NS * kPairStageBytes;
+    uint8_t* q_res = smem + (size_t)NS * kPairStageBytes;  // resident half query tile (RES only)
+    uint8_t* tail = q_res + (RES ? (size_t)KC * kQHalfBytes : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* q_bar = tmem_empty + 2;  // leader: own bytes + the peer's forward; peer: own bytes
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(q_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int64_t pair = blockIdx.x >> 1;
     const int64_t n_pairs = gridDim.x >> 1;
-    constexpr uint32_t kTmemCols = 512;
+    constexpr uint32_t kTmemCols = 2 * PQ;  // two accumulator stages of PQ columns
     const int n_qt = (int)((a.nq + kPairQ - 1) / kPairQ);
     // work item w = (pair of walk positions, 256-query tile), query tile fastest; every cluster takes
     // one contiguous, equally sized range of w, so small levels still occupy all SM pairs
@@ -627,6 +641,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EpiCfg<kPairQ>::kWarps); }
+        mbar_init(q_bar, rank == 0 ? 2 : 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc2(tmem_holder, kTmemCols);
@@ -642,6 +657,11 @@ scan_tc_pair_kernel(const ScanArgs a) {
             const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy == 2 ? policy_evict_last() : policy_evict_normal());
             const uint64_t pol_q = policy_evict_last();
             if (a.q_dep) pdl_wait();
+            if (RES) {  // the batch is one query tile: this CTA's half stays in shared memory for the whole launch
+                mbar_expect_tx(q_bar, (uint32_t)(KC * kQHalfBytes));
+                bulk_g2s(q_res, a.qshadow + (size_t)rank * ((size_t)a.d * kPairHalfQ * 2), (uint32_t)(KC * kQHalfBytes),
+                         q_bar, pol_q);
+            }
             int s = 0;
             uint32_t ph = 0;
             for (int64_t w = w_lo; w < w_hi; ++w) {
@@ -658,8 +678,8 @@ scan_tc_pair_kernel(const ScanArgs a) {
                     uint8_t* dst = stage_base + (size_t)s * kPairStageBytes;
                     mbar_expect_tx(&full_bar[s], (uint32_t)kPairStageBytes);
                     bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
-                    bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * (kPairHalfQ * 128), kPairHalfQ * 128,
-                             &full_bar[s], pol_q);
+                    if (!RES)
+                        bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s], pol_q);
                     if (++s == NS) { s = 0; ph ^= 1u; }
                 }
             }
@@ -670,6 +690,10 @@ scan_tc_pair_kernel(const ScanArgs a) {
             uint32_t ph = 0;
             if (rank == 1) {
                 // ============================= forwarder =============================
+                if (RES) {
+                    mbar_wait(q_bar, 0, 650);                       // this CTA's half of the query tile has landed
+                    mbar_arrive_cluster(map_to_rank(q_bar, 0));     // tell the leader
+                }
                 for (int64_t w = w_lo; w < w_hi; ++w) {
                     for (int kc = 0; kc < KC; ++kc) {
                         mbar_wait(&full_bar[s], ph, 600 + s);               // this CTA's stage has landed
@@ -680,6 +704,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
             } else {
                 // ================================ MMA ================================
                 constexpr uint32_t idesc = make_idesc_bf16(2 * kTileRows, kPairQ);
+                if (RES) mbar_wait(q_bar, 0, 200);  // both halves of the query tile are resident
                 uint32_t it = 0;
                 for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
                     const uint32_t as = it & 1u;
@@ -692,7 +717,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
                         tc_fence_after();
                         const uint32_t xa = smem_u32(stage_base + (size_t)s * kPairStageBytes);
                         const uint64_t da = make_sw128_desc(xa);
-                        const uint64_t db = make_sw128_desc(xa + kBlockBytes);
+                        const uint64_t db = make_sw128_desc(RES ? smem_u32(q_res + (size_t)kc * kQHalfBytes) : xa + kBlockBytes);
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
                             umma_bf16_2cta(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
@@ -717,7 +742,9 @@ scan_tc_pair_kernel(const ScanArgs a) {
         Stash pend, cur;
         stash_clear(pend);
         pdl_wait();
-        const float no_tau[NG] = {};
+        float mytau[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) mytau[g] = RES ? __ldcg(a.tau + col0 + g * 32 + lane) : 0.f;  // RES: one query tile
         for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
             const int64_t p = w / n_qt;
             const int qt = (int)(w - p * n_qt);
@@ -731,8 +758,8 @@ scan_tc_pair_kernel(const ScanArgs a) {
             mbar_wait(&tmem_full[as], aph, 500 + as);
             tc_fence_after();
             const uint32_t ebar = leader_empty[as];
-            filter_item<NG, false>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
-                            lane, cur, no_tau, [=]() {
+            filter_item<NG, RES>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
+                            lane, cur, mytau, [=]() {
                                 tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_cluster(ebar);
@@ -777,14 +804,28 @@ static int env_flag(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+template <int PQ, bool RES>
+static size_t pair_fixed_bytes(int d) {
+    return 1024 + (2 * kMaxStages + 5) * 8 + 16 + (RES ? (size_t)(d / 64) * PairCfg<PQ, RES>::kQHalfBytes : 0);
+}
+template <int PQ, bool RES>
+static int pair_stages(int d) {
+    int ns = kMaxStages;
+    while (ns > 0 && pair_fixed_bytes<PQ, RES>(d) + (size_t)ns * PairCfg<PQ, RES>::kStageBytes > (size_t)kSmemLimit) --ns;
+    return ns;
+}
+
 int scan_tc_pick(int64_t nq, int d, ScanTcPlan* plan) {
     KIRAG_CHECK(scan_tc_supported(d), "scan_tc: dimension %d is not supported (need a multiple of 64, <= 4096)", d);
+    const int pair_ok = env_flag("KIRAG_SCAN_PAIR", 1) ? 1 : 0;
     plan->pair = 0;
     if (nq <= 32 && pick_stages(32, true, d) >= 4) { plan->bq = 32; plan->resident = 1; }
+    else if (nq <= 64 && pick_stages(64, true, d) >= 4) { plan->bq = 64; plan->resident = 1; }  // 128 KB of queries + >= 4 stages
     else if (nq <= 64) { plan->bq = 64; plan->resident = 0; }
+    else if (nq <= 128 && pair_ok && pair_stages<128, true>(d) >= 4) { plan->bq = 128; plan->resident = 1; plan->pair = 1; }
     else if (nq <= 128) { plan->bq = 128; plan->resident = 0; }
-    else { plan->bq = 256; plan->resident = 0; plan->pair = env_flag("KIRAG_SCAN_PAIR", 1) ? 1 : 0; }
-    plan->q_tile_rows = plan->pair ? kPairHalfQ : plan->bq;
+    else { plan->bq = 256; plan->resident = 0; plan->pair = pair_ok; }
+    plan->q_tile_rows = plan->pair ? plan->bq / 2 : plan->bq;
     return 0;
 }
 
@@ -793,19 +834,19 @@ size_t scan_tc_qshadow_bytes(int64_t nq, int d, const ScanTcPlan& plan) {
     return (size_t)tiles * plan.bq * d * 2;
 }
 
+template <int PQ, bool RES>
 static int launch_scan_pair(const ScanArgs& args_in, int num_sms, cudaStream_t st) {
     ScanArgs args = args_in;
-    int ns = kMaxStages;
-    const size_t fixed = 1024 + (2 * kMaxStages + 4) * 8 + 16;
-    while (ns > 0 && fixed + (size_t)ns * kPairStageBytes > (size_t)kSmemLimit) --ns;
+    const int ns = pair_stages<PQ, RES>(args.d);
     KIRAG_CHECK(ns >= 2, "scan_tc pair: no room for a shared-memory pipeline");
+    KIRAG_CHECK(!RES || args.nq <= PQ, "scan_tc pair: the resident variant takes a single query tile");
     args.n_stages = ns;
-    const size_t smem = fixed + (size_t)ns * kPairStageBytes;
-    if (ensure_dynamic_smem(scan_tc_pair_kernel, kSmemLimit)) return 1;
-    int64_t pairs = ((args.tile_hi - args.tile_lo + 1) / 2) * ((args.nq + kPairQ - 1) / kPairQ);  // work items
+    const size_t smem = pair_fixed_bytes<PQ, RES>(args.d) + (size_t)ns * PairCfg<PQ, RES>::kStageBytes;
+    if (ensure_dynamic_smem(scan_tc_pair_kernel<PQ, RES>, kSmemLimit)) return 1;
+    int64_t pairs = ((args.tile_hi - args.tile_lo + 1) / 2) * ((args.nq + PQ - 1) / PQ);  // work items
     if (pairs > num_sms / 2) pairs = num_sms / 2;
     if (pairs <= 0) return 0;
-    KIRAG_CUDA_OK(launch_chained(scan_tc_pair_kernel, dim3((unsigned)(2 * pairs)), dim3(EpiCfg<kPairQ>::kThreads), smem, st, args));
+    KIRAG_CUDA_OK(launch_chained(scan_tc_pair_kernel<PQ, RES>, dim3((unsigned)(2 * pairs)), dim3(EpiCfg<PQ>::kThreads), smem, st, args));
     KIRAG_LAUNCH_OK("scan_tc_pair_kernel");
     return 0;
 }
@@ -827,8 +868,10 @@ static int launch_scan_t(const ScanArgs& args_in, int num_sms, cudaStream_t st) 
 }
 
 static int launch_scan_args(const ScanArgs& args, const ScanTcPlan& plan, int num_sms, cudaStream_t st) {
-    if (plan.pair) return launch_scan_pair(args, num_sms, st);
+    if (plan.pair && plan.bq == 256 && !plan.resident) return launch_scan_pair<256, false>(args, num_sms, st);
+    if (plan.pair && plan.bq == 128 && plan.resident) return launch_scan_pair<128, true>(args, num_sms, st);
     if (plan.bq == 32 && plan.resident) return launch_scan_t<32, true>(args, num_sms, st);
+    if (plan.bq == 64 && plan.resident) return launch_scan_t<64, true>(args, num_sms, st);
     if (plan.bq == 64 && !plan.resident) return launch_scan_t<64, false>(args, num_sms, st);
     if (plan.bq == 128 && !plan.resident) return launch_scan_t<128, false>(args, num_sms, st);
     if (plan.bq == 256 && !plan.resident) return launch_scan_t<256, false>(args, num_sms, st);

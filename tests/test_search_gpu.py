@@ -134,7 +134,11 @@ def test_auto_path_integer_data_bit_exact(fa, n, d, nq, k):
 
 
 @pytest.mark.parametrize("n,d,nq,k", [(100000, 128, 16, 10), (50000, 1024, 8, 20), (200000, 64, 64, 100),
-                                      (60000, 1024, 256, 20), (30000, 768, 1, 10)])
+                                      (60000, 1024, 256, 20), (30000, 768, 1, 10),
+                                      # every kernel variant of the filter scan: resident 64-query tile,
+                                      # 2-CTA resident 128-query tile (65..128 queries), 2-CTA 256-query tiles
+                                      (70000, 1024, 64, 10), (80000, 1024, 100, 10), (50000, 256, 128, 20),
+                                      (40000, 1024, 65, 20), (40000, 1024, 700, 10)])
 def test_auto_path_unit_vectors_uses_the_filter(fa, n, d, nq, k):
     rng = np.random.default_rng(n + k)
     xb, xq = unit_rows(rng, n, d), unit_rows(rng, nq, d)
