@@ -260,9 +260,9 @@ def measure_batch(sh, lib, q_all, batch, k, steps, warmup, device, dist_ok, peak
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"]}
     # dram__bytes_read.sum + dram__bytes_write.sum of the scan launches of one step, from the committed
-    # `ncu --set full` capture of this very workload (profiles/r01_scan_traffic.json); null otherwise
+    # `ncu --set full` capture of this very workload (profiles/r01b_scan_traffic.json); null otherwise
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_scan_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01b_scan_traffic.json")
     if world == 1 and rows_total == 21_000_000 and k == 100 and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(str(batch), {}).get("dram_bytes_per_step")
     roof.update({"traffic": traffic, "traffic_note": "bytes per step (all scan launches of one step), ncu capture",
