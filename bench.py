@@ -314,6 +314,22 @@ def run_ours(args):
     head = measure_batch(sh, lib, q_all, B, k, args.steps, args.warmup, device, dist_ok, peaks, args.rows, world)
     clocks = sampler.stop() if rank == 0 else None
 
+    # where a multi-GPU step goes: every rank's LOCAL search time (no exchange) and the exchange alone.  The step
+    # is paced by the slowest rank (GPUs of one box sit at different power-capped clocks), so max(local) + exchange
+    # ~ ms_per_step explains the scaling loss that is not kernel time.
+    rank_diag = None
+    if dist_ok:
+        qh = q_all[:B].contiguous()
+        local_ms = timed_steps(lambda: sh.search_local(qh, k), max(3, min(args.steps, 5)), 2, device, False)
+        D_loc, I_loc = sh.search_local(qh, k)
+        exch = (lambda: sh.peer.merge(D_loc, I_loc)) if sh.peer is not None else (lambda: sh.search(qh, k))
+        exch_ms = timed_steps(exch, 10, 3, device, True) if sh.peer is not None else None
+        t = torch.tensor([local_ms], dtype=torch.float64, device=device)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_diag = {"local_search_ms_per_rank": [round(float(x.item()), 3) for x in allt],
+                     "exchange_merge_ms": exch_ms}
+
     # end to end through the reference-facing call with HOST buffers (rank-local shard; for N > 1 the
     # exchange + merge are included through the device path and the final result is copied out)
     q_host = torch.empty((B, D_MODEL), dtype=torch.float32, pin_memory=True)
@@ -339,7 +355,9 @@ def run_ours(args):
     for b in sweep:
         if b == B:
             continue
-        r = measure_batch(sh, lib, q_all, b, k, max(3, min(args.steps, 5)), 3, device, dist_ok, peaks, args.rows, world)
+        # short steps right after the power-capped headline phase: warm up longer so that the clocks have settled
+        r = measure_batch(sh, lib, q_all, b, k, max(3, min(args.steps, 5)), 10 if b <= 1024 else 3, device, dist_ok,
+                          peaks, args.rows, world)
         sweep_out.append({"batch": b, "qps": r["qps"], "ms_per_step": r["ms_per_step"],
                           "roofline_bound": r["roofline"]["bound"], "roofline_frac": r["roofline"]["frac"],
                           "roofline_achieved": r["roofline"]["achieved"], "roofline_unit": r["roofline"]["unit"],
@@ -378,6 +396,7 @@ def run_ours(args):
             "gpu_launches": (int(head["stats"].get("kernel_launches", 0)) + (1 if world > 1 else 0)) * args.steps,
             "clocks": clocks,
             "search_stats": head["stats"],
+            "rank_diag": rank_diag,
             "sweep": sweep_out,
         }
         emit(line)

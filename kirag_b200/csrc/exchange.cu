@@ -46,6 +46,8 @@ struct ExchangeArgs {
     const int64_t* I_loc;
     float* D_out;
     int64_t* I_out;
+    int vec16;     // rows can be copied with 16-byte accesses (k % 4 == 0, aligned bases)
+    int n_groups;  // thread groups per CTA in the merge phase (1, 2 or 4), one query each at a time
 };
 
 __device__ __forceinline__ uint8_t* slot_ptr(const ExchangeArgs& a, int dst, int src) {
@@ -78,27 +80,43 @@ __device__ __forceinline__ int count_before(const uint32_t* keys, const int64_t*
     return lo;
 }
 
-__global__ void __launch_bounds__(512, 2) exchange_merge_kernel(const ExchangeArgs a) {
+__device__ __forceinline__ void group_barrier(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+constexpr int kExchangeThreads = 512;
+
+__global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(const ExchangeArgs a) {
     extern __shared__ uint64_t xsmem[];
     const int G = a.G, k = a.k;
-    int64_t* ids = reinterpret_cast<int64_t*>(xsmem);            // [G * k]
-    uint32_t* keys = reinterpret_cast<uint32_t*>(ids + G * k);   // [G * k]
-    __shared__ int n_valid[kMaxRanks];
+    const int L = G * k;
+    __shared__ int n_valid_all[4][kMaxRanks];
     const int b = blockIdx.x, NB = gridDim.x;
     const int64_t q_lo = a.nq * b / NB, q_hi = a.nq * (b + 1) / NB;
     const int64_t e_lo = q_lo * k, e_hi = q_hi * k;
 
     // ------------------------------------------------------------------ push ----
     // peers are visited in a rank-rotated order so that the G ranks do not all hit the same
-    // destination at the same time
+    // destination at the same time; 16-byte stores when the rows allow it
     for (int p = 0; p < G; ++p) {
         const int dst = (a.rank + p) % G;
         uint8_t* slot = slot_ptr(a, dst, a.rank);
         float* sd = reinterpret_cast<float*>(slot);
         int64_t* si = reinterpret_cast<int64_t*>(slot + a.ids_off);
-        for (int64_t i = e_lo + threadIdx.x; i < e_hi; i += blockDim.x) {
-            sd[i] = a.D_loc[i];
-            si[i] = a.I_loc[i];
+        if (a.vec16) {
+            const float4* srcd = reinterpret_cast<const float4*>(a.D_loc + e_lo);
+            float4* dstd = reinterpret_cast<float4*>(sd + e_lo);
+            const int64_t nd = (e_hi - e_lo) >> 2;
+            for (int64_t i = threadIdx.x; i < nd; i += blockDim.x) dstd[i] = srcd[i];
+            const longlong2* srci = reinterpret_cast<const longlong2*>(a.I_loc + e_lo);
+            longlong2* dsti = reinterpret_cast<longlong2*>(si + e_lo);
+            const int64_t ni = (e_hi - e_lo) >> 1;
+            for (int64_t i = threadIdx.x; i < ni; i += blockDim.x) dsti[i] = srci[i];
+        } else {
+            for (int64_t i = e_lo + threadIdx.x; i < e_hi; i += blockDim.x) {
+                sd[i] = a.D_loc[i];
+                si[i] = a.I_loc[i];
+            }
         }
     }
     __syncthreads();
@@ -125,11 +143,19 @@ __global__ void __launch_bounds__(512, 2) exchange_merge_kernel(const ExchangeAr
     }
     __syncthreads();
     // ----------------------------------------------------------------- merge ----
-    const int L = G * k;
-    for (int64_t q = q_lo; q < q_hi; ++q) {
-        if (threadIdx.x < G) n_valid[threadIdx.x] = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    // The CTA splits into n_groups thread groups; each merges one query at a time in its own slice of
+    // shared memory and synchronises with a named barrier of its own.
+    const int n_groups = a.n_groups;
+    const int gthreads = kExchangeThreads / n_groups;
+    const int grp = threadIdx.x / gthreads;
+    const int gt = threadIdx.x - grp * gthreads;
+    int64_t* ids = reinterpret_cast<int64_t*>(xsmem) + (size_t)grp * L;                        // [L]
+    uint32_t* keys = reinterpret_cast<uint32_t*>(reinterpret_cast<int64_t*>(xsmem) + (size_t)n_groups * L) + (size_t)grp * L;  // [L]
+    int* n_valid = n_valid_all[grp];
+    for (int64_t q = q_lo + grp; q < q_hi; q += n_groups) {
+        if (gt < G) n_valid[gt] = 0;
+        group_barrier(1 + grp, gthreads);
+        for (int i = gt; i < L; i += gthreads) {
             const int g = i / k, j = i - g * k;
             const uint8_t* slot = slot_ptr(a, a.rank, g);
             const int64_t id = __ldcg(reinterpret_cast<const int64_t*>(slot + a.ids_off) + q * k + j);
@@ -140,10 +166,10 @@ __global__ void __launch_bounds__(512, 2) exchange_merge_kernel(const ExchangeAr
             ids[i] = ok ? id : INT64_MAX;
             if (ok) atomicAdd(&n_valid[g], 1);  // valid items form a prefix of each list
         }
-        __syncthreads();
+        group_barrier(1 + grp, gthreads);
         int total = 0;
         for (int g = 0; g < G; ++g) total += n_valid[g];
-        for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        for (int i = gt; i < L; i += gthreads) {
             const int g = i / k, j = i - g * k;
             if (j >= n_valid[g]) continue;
             const uint32_t key = keys[i];
@@ -156,11 +182,11 @@ __global__ void __launch_bounds__(512, 2) exchange_merge_kernel(const ExchangeAr
                 a.I_out[q * k + r] = id;
             }
         }
-        for (int j = total + threadIdx.x; j < k; j += blockDim.x) {  // fewer than k results in total
+        for (int j = total + gt; j < k; j += gthreads) {  // fewer than k results in total
             a.D_out[q * k + j] = -FLT_MAX;
             a.I_out[q * k + j] = -1;
         }
-        __syncthreads();
+        group_barrier(1 + grp, gthreads);
     }
 }
 
@@ -333,10 +359,15 @@ int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int
     a.I_out = I_out;
     // the grid must be the same on every rank (flags are per block): derived from nq only
     int blocks = (int)(nq < kExchangeMaxBlocks ? nq : kExchangeMaxBlocks);
-    const size_t smem = (size_t)x->world * k * 12;
-    if (smem > 48 * 1024 && ensure_dynamic_smem(exchange_merge_kernel, 8192 * 12)) return 1;
-    int threads = 512;
-    exchange_merge_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(a);
+    const size_t per_query = (size_t)x->world * k * 12;
+    int n_groups = 4;
+    while (n_groups > 1 && per_query * n_groups > 96 * 1024) n_groups >>= 1;
+    a.n_groups = n_groups;
+    a.vec16 = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(D_loc) & 15) == 0) &&
+              ((reinterpret_cast<uintptr_t>(I_loc) & 15) == 0) && ((a.ids_off & 15) == 0);
+    const size_t smem = per_query * n_groups;
+    if (smem > 48 * 1024 && ensure_dynamic_smem(exchange_merge_kernel, 96 * 1024)) return 1;
+    exchange_merge_kernel<<<blocks, kExchangeThreads, smem, (cudaStream_t)stream>>>(a);
     KIRAG_LAUNCH_OK("exchange_merge_kernel");
     return 0;
 }
