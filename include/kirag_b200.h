@@ -154,6 +154,14 @@ int kirag_index_load(const char* path, int device, kirag_index_t** out);
  * [ntotal, d]. */
 int kirag_index_device_ptrs(const kirag_index_t* h, const float** master_f32, const void** shadow_bf16);
 
+/* Test hook (host only, no device needed): the level schedule of the filter path for a search of nq queries
+ * over n_rows rows: rows_hi_out[l] = number of corpus rows covered after level l (the last entry is n_rows).
+ * Returns the number of levels (> 0), -1 if the shape is not eligible for the filter path (exact scan),
+ * -2 (kirag_last_error() set) on a bad argument.  cap_out: candidate-buffer entries per query;
+ * kprime_out: the over-fetch k' = max(4k, 32). */
+int kirag_debug_level_schedule(int64_t n_rows, int64_t nq, int k, int d, int64_t* rows_hi_out, int max_levels,
+                               int* cap_out, int* kprime_out);
+
 /* Test hook: dense approximate scores of the bf16 tcgen05 scan, written to a
  * host buffer laid out [ntotal, nq].  Used by the parity tests to check the
  * tensor-core contraction in isolation from the top-k logic. */

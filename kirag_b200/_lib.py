@@ -68,6 +68,8 @@ SIGNATURES = {
     "kirag_index_save": (c_int, [c_void_p, c_char_p]),
     "kirag_index_load": (c_int, [c_char_p, c_int, POINTER(c_void_p)]),
     "kirag_index_device_ptrs": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
+    "kirag_debug_level_schedule": (c_int, [c_int64, c_int64, c_int, c_int, POINTER(c_int64), c_int, POINTER(c_int),
+                                           POINTER(c_int)]),
     "kirag_index_debug_scores": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "kirag_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "kirag_exchange_create": (c_int, [c_int, c_int, c_int, c_int64, c_int, POINTER(c_void_p)]),

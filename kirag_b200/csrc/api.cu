@@ -866,6 +866,37 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
     return rc;
 }
 
+/* host-only: the level schedule fast_search() would use (no device needed) */
+int kirag_debug_level_schedule(int64_t n_rows, int64_t nq, int k, int d, int64_t* rows_hi_out, int max_levels,
+                               int* cap_out, int* kprime_out) {
+    if (!(n_rows > 0 && nq > 0 && k > 0 && rows_hi_out && max_levels > 0)) {
+        set_error("debug_level_schedule: bad argument");
+        return -2;
+    }
+    int64_t kp = (int64_t)4 * k;
+    if (kp < 32) kp = 32;
+    if (kp > 2048 || !scan_tc_supported(d) || n_rows > 0x7fffff00LL) return -1;  // not eligible for the filter path
+    FastParams fp{};
+    fp.kprime = (int)kp;
+    fp.growth_override = env_int("KIRAG_LEVEL_GROWTH", 0);
+    fp.cap_override = env_int("KIRAG_CAND_CAP", 0);
+    if (fp.cap_override > 0 && fp.cap_override < 4 * kp) return -1;
+    const int cap = pick_cap(fp, nq);
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    const std::vector<int64_t> b = level_bounds(n_tiles, cap, fp);
+    if ((int)b.size() > max_levels) {
+        set_error("debug_level_schedule: %zu levels do not fit in %d slots", b.size(), max_levels);
+        return -2;
+    }
+    for (size_t i = 0; i < b.size(); ++i) {
+        const int64_t r = b[i] * kTileRows;
+        rows_hi_out[i] = r < n_rows ? r : n_rows;
+    }
+    if (cap_out) *cap_out = cap;
+    if (kprime_out) *kprime_out = (int)kp;
+    return (int)b.size();
+}
+
 int kirag_index_device_ptrs(const kirag_index_t* h, const float** master_f32, const void** shadow_bf16) {
     KIRAG_CHECK(h != nullptr, "index_device_ptrs: null index");
     if (master_f32) *master_f32 = h->master;

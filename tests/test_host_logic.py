@@ -136,3 +136,59 @@ def test_contiguous_sampler_covers_everything_once():
         for world in (1, 3, 8):
             seen = [i for r in range(world) for i in ContiguousShardSampler(n, r, world)]
             assert seen == list(range(n))
+
+
+# ------------------------------------------------------------- level schedule ---
+def _schedule(n_rows, nq, k, d=1024):
+    import ctypes
+
+    from kirag_b200 import _lib
+
+    lib = _lib.load()
+    out = (ctypes.c_int64 * 64)()
+    cap, kp = ctypes.c_int(), ctypes.c_int()
+    n = lib.kirag_debug_level_schedule(n_rows, nq, k, d, out, 64, ctypes.byref(cap), ctypes.byref(kp))
+    return n, [int(out[i]) for i in range(max(n, 0))], cap.value, kp.value
+
+
+@pytest.mark.parametrize("n_rows", [1, 127, 128, 129, 4096, 20_000, 100_000, 430_000, 2_625_000, 5_200_000, 21_000_000])
+@pytest.mark.parametrize("nq,k", [(1, 10), (2, 100), (32, 100), (64, 20), (128, 100), (129, 100), (1024, 10), (4096, 100),
+                                  (16384, 512)])
+def test_level_schedule_covers_the_corpus_with_bounded_growth(n_rows, nq, k):
+    """The filter path's level schedule (csrc/api.cu::level_bounds), a pure host function: strictly
+    increasing, ends at the whole corpus, level 0 is half the candidate buffer, later levels never
+    grow the prefix by more than cap / (4 k') (expected survivors stay below a quarter of the buffer)."""
+    n, hi, cap, kp = _schedule(n_rows, nq, k)
+    assert n == len(hi) and n >= 1
+    assert kp == max(4 * k, 32)
+    assert cap == (32768 if nq <= 128 else 8192)
+    assert hi[-1] == n_rows
+    assert all(a < b for a, b in zip(hi, hi[1:]))
+    assert hi[0] == min(n_rows, cap // 2)
+    gmax = max(2, min(32, cap // (4 * kp)))
+    tiles = [-(-h // 128) for h in hi]
+    for lvl, (a, b) in enumerate(zip(tiles, tiles[1:]), start=1):
+        limit = min(4, gmax) if lvl == 1 else gmax
+        assert b <= a * limit + 1, (lvl, a, b, limit)  # +1 tile: ceil of the geometric step
+    # and it does not use more levels than a greedy walk with the same limits would
+    t, greedy = tiles[0], 1
+    n_tiles = tiles[-1]
+    if t < n_tiles:
+        t, greedy = min(n_tiles, t * min(4, gmax)), 2
+    while t < n_tiles:
+        t, greedy = min(n_tiles, t * gmax), greedy + 1
+    assert n <= greedy
+
+
+def test_level_schedule_reference_points():
+    # the shapes DESIGN.md quotes
+    assert _schedule(21_000_000, 4096, 100)[0] == 7
+    assert _schedule(21_000_000, 32, 100)[0] == 4
+    assert _schedule(2_625_000, 4096, 100)[0] == 6
+    assert _schedule(430_000, 64, 20)[0] == 3
+    assert _schedule(1000, 4, 10)[1] == [1000]
+
+
+def test_level_schedule_ineligible_shapes():
+    assert _schedule(1000, 4, 10, d=100)[0] == -1      # d not a multiple of 64: exact scan only
+    assert _schedule(1000, 4, 1024)[0] == -1           # k' = 4096 > 2048
