@@ -178,8 +178,9 @@ struct kirag_index {
     int64_t capacity = 0;       // rows
     float* master = nullptr;    // [capacity, d] fp32
     uint8_t* shadow = nullptr;  // bf16 tiles, capacity rounded up to 128 rows (null if d % 64)
-    unsigned* maxnorm2_bits = nullptr;
-    float maxnorm = 0.f;
+    unsigned* maxnorm2_bits = nullptr;  // device: [0] max ||x||^2, [1] max ||x - bf16(x)||^2 (float bits)
+    float maxnorm = 0.f;                // max_j ||x_j||
+    float maxerr = 0.f;                 // max_j ||x_j - bf16(x_j)||
     // workspaces (grow-only)
     DevBuf q_dev, D_dev, I_dev, qshadow, qnorm, cand, cnt, tau, overflow, flags, rescored;
     DevBuf dense, stage_a, stage_b, qmap, qsel, qnorm2;
@@ -283,7 +284,7 @@ static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, 
         }
         if (launch_final(cur, cur_stride, nullptr, nullptr, cur_count, cur_count, gq, k,
                          qmap_dev ? D : D + (out_row0 + g0) * k, qmap_dev ? I : I + (out_row0 + g0) * k,
-                         id_offset, nullptr, nullptr, 0.f, 0, nullptr, nullptr,
+                         id_offset, nullptr, nullptr, nullptr, 0.f, 0.f, 0, nullptr, nullptr,
                          qmap_dev ? qmap_dev + g0 : nullptr, st)) return 1;
     }
     return 0;
@@ -377,6 +378,24 @@ static int64_t pick_tile_mult(int64_t n_tiles) {
     return m % n_tiles;
 }
 
+// Exactness certificate, the bound on |approx - canonical| for any corpus row j and query q.  With
+// x~ = bf16(x), q~ = bf16(q):  <x~,q~> - <x,q> = <x~ - x, q~> + <x, q~ - q>, so
+//   |.| <= ||x_j - x~_j|| (||q|| + ||q - q~||) + ||x_j|| ||q - q~||
+// plus the fp32 accumulation error of both dot products (d * 2^-21 ||x|| ||q|| is generous: the bf16
+// products are exact in fp32, sequential rounding costs at most d * 2^-24 per unit of ||x|| ||q||, a
+// truncating accumulator twice that).  The rounding-error norms are MEASURED when rows / queries
+// are converted (convert.cu), not bounded by 2^-9 ||x||: for typical data they are ~0.58 * 2^-9 ||x||,
+// which makes eps ~1.4x tighter than the worst case.  eps(q) = a * ||q|| + b * ||q - q~||, 0.2 % slack
+// for the fp32 evaluation of the norms themselves.
+struct CertEps { float a, b; };
+static CertEps cert_eps(const kirag_index* h) {
+    const double xn = (double)h->maxnorm, ex = (double)h->maxerr;
+    CertEps e;
+    e.a = (float)((ex + (double)h->d * ldexp(1.0, -21) * xn) * 1.002);
+    e.b = (float)((xn + 2.0 * ex) * 1.002);
+    return e;
+}
+
 static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float* D, int64_t* I,
                        int64_t id_offset, const FastParams& fp, int check_cert, int* levels_out,
                        cudaStream_t st) {
@@ -390,7 +409,7 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     if (scan_tc_pick(nq, d, &plan)) return 1;
     const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
     if (h->qshadow.ensure(qs_bytes)) return 1;
-    if (h->qnorm.ensure((size_t)nq * 4)) return 1;
+    if (h->qnorm.ensure((size_t)nq * 8)) return 1;  // [nq] norms, then [nq] bf16 rounding-error norms
     const int cap = pick_cap(fp, nq);
     if (h->cand.ensure((size_t)nq * cap * sizeof(Cand))) return 1;
     if (h->cnt.ensure((size_t)nq * 4)) return 1;
@@ -405,7 +424,8 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
                                  h->tau.as<float>(), h->cnt.as<int>(), h->overflow.as<int>(), nq, nq_pad));
     KIRAG_LAUNCH_OK("init_search_state_kernel");
     prof_mark(0, st);
-    if (launch_convert_rows(qd, nq, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, h->qnorm.as<float>(), st)) return 1;
+    if (launch_convert_rows(qd, nq, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, h->qnorm.as<float>(),
+                            h->qnorm.as<float>() + nq, st)) return 1;
     prof_mark(1, st);
 
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
@@ -441,12 +461,10 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), cap, fp.kprime,
                        h->rescored.as<float>(), nq, st)) return 1;
     prof_mark(50, st);
-    // eps bounds |approx - canonical|: bf16 rounding of both operands (2 * 2^-9, plus
-    // the cross term) and fp32 accumulation slack, times ||q|| * max_j ||x_j||
-    const float eps_factor = (float)((ldexp(1.0, -8) * 1.002 + (double)d * ldexp(1.0, -21)) * (double)h->maxnorm);
+    const CertEps ce = cert_eps(h);
     if (launch_final(h->cand.as<Cand>(), cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, fp.kprime,
-                     (int)nq, k, D, I, id_offset, h->tau.as<float>(), h->qnorm.as<float>(), eps_factor,
-                     check_cert, h->overflow.as<int>(), h->flags.as<int>(), nullptr, st)) return 1;
+                     (int)nq, k, D, I, id_offset, h->tau.as<float>(), h->qnorm.as<float>(), h->qnorm.as<float>() + nq,
+                     ce.a, ce.b, check_cert, h->overflow.as<int>(), h->flags.as<int>(), nullptr, st)) return 1;
     prof_mark(51, st);
     if (levels_out) *levels_out = levels;
     return 0;
@@ -455,7 +473,8 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
 // tau2[i] = (k-th canonical score of flagged query i) - eps_i : every row of the true top-k has an
 // approximate score >= tau2 (certificate); a query without k results gets -inf
 __global__ void rescan_threshold_kernel(const float* __restrict__ D, const int* __restrict__ qmap,
-                                        const float* __restrict__ qnorm, int k, float eps_factor, int64_t nb,
+                                        const float* __restrict__ qnorm, const float* __restrict__ qerr, int k,
+                                        float eps_a, float eps_b, int64_t nb,
                                         int64_t nb_pad, float* __restrict__ tau2, int* __restrict__ cnt,
                                         int* __restrict__ overflow) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,7 +482,7 @@ __global__ void rescan_threshold_kernel(const float* __restrict__ D, const int* 
     if (i >= nb) { tau2[i] = INFINITY; return; }
     const int q = qmap[i];
     const float kth = D[(int64_t)q * k + (k - 1)];
-    tau2[i] = (kth > -FLT_MAX) ? kth - eps_factor * qnorm[q] : -INFINITY;
+    tau2[i] = (kth > -FLT_MAX) ? kth - (eps_a * qnorm[q] + eps_b * qerr[q]) : -INFINITY;
     cnt[i] = 0;
     overflow[i] = 0;
 }
@@ -473,7 +492,8 @@ __global__ void rescan_threshold_kernel(const float* __restrict__ D, const int* 
 // candidate is rescored in fp32.  Exact by construction; only a buffer overflow (more than `cap`
 // rows within eps of the k-th score) is left to the exact fp32 scan.  qsel: the flagged queries
 // gathered contiguously; qmap: their row numbers in D/I.  still_bad (host) receives the overflowed ones.
-static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_all, int64_t nb, int k, float* D,
+static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_all, const float* qerr_all, int64_t nb,
+                         int k, float* D,
                          int64_t* I, const int* qmap_dev, int64_t id_offset, int cap, std::vector<int>* still_bad,
                          cudaStream_t st) {
     const int d = h->d;
@@ -487,13 +507,14 @@ static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_a
     if (h->cnt.ensure((size_t)nb_pad * 4) || h->tau.ensure((size_t)nb_pad * 4) || h->overflow.ensure((size_t)nb_pad * 4)) return 1;
     if (h->flags.ensure((size_t)nb_pad * 4)) return 1;
     if (h->rescored.ensure((size_t)nb * cap * 4)) return 1;
-    const float eps_factor = (float)((ldexp(1.0, -8) * 1.002 + (double)d * ldexp(1.0, -21)) * (double)h->maxnorm);
+    const CertEps ce = cert_eps(h);
     // thresholds from the first-attempt results (still in D), before anything is overwritten
     rescan_threshold_kernel<<<(unsigned)((nb_pad + 255) / 256), 256, 0, st>>>(
-        D, qmap_dev, qnorm_all, k, eps_factor, nb, nb_pad, h->tau.as<float>(), h->cnt.as<int>(), h->overflow.as<int>());
+        D, qmap_dev, qnorm_all, qerr_all, k, ce.a, ce.b, nb, nb_pad, h->tau.as<float>(), h->cnt.as<int>(),
+        h->overflow.as<int>());
     KIRAG_LAUNCH_OK("rescan_threshold_kernel");
     if ((nb % plan.bq) != 0) KIRAG_CUDA_OK(cudaMemsetAsync(h->qshadow.p, 0, qs_bytes, st));
-    if (launch_convert_rows(qsel, nb, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, nullptr, st)) return 1;
+    if (launch_convert_rows(qsel, nb, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, nullptr, nullptr, st)) return 1;
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
     if (launch_scan_tc(h->shadow, n, d, h->qshadow.p, nb, plan, 0, n_tiles, n_tiles, 1, h->tau.as<float>(),
                        h->cand.as<Cand>(), h->cnt.as<int>(), cap, h->num_sms, 1, st)) return 1;
@@ -502,7 +523,7 @@ static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_a
     std::vector<int> counts((size_t)nb);
     KIRAG_CUDA_OK(cudaMemcpyAsync(counts.data(), h->cnt.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
     if (launch_final(h->cand.as<Cand>(), cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, cap, (int)nb, k, D, I,
-                     id_offset, nullptr, nullptr, 0.f, 0, nullptr, nullptr, qmap_dev, st)) return 1;
+                     id_offset, nullptr, nullptr, nullptr, 0.f, 0.f, 0, nullptr, nullptr, qmap_dev, st)) return 1;
     KIRAG_CUDA_OK(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < nb; ++i)
         if (counts[(size_t)i] > cap) still_bad->push_back((int)i);
@@ -581,14 +602,15 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
                     const int64_t nb = (int64_t)rescan.size();
                     if (h->qmap.ensure((size_t)nb * 4)) return 1;
                     if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
-                    if (h->qnorm2.ensure((size_t)cq * 4)) return 1;
-                    // qnorm / flags buffers are reused by the rescan: keep a copy of the norms
-                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qnorm2.p, h->qnorm.p, (size_t)cq * 4, cudaMemcpyDeviceToDevice, st));
+                    if (h->qnorm2.ensure((size_t)cq * 8)) return 1;
+                    // qnorm / flags buffers are reused by the rescan: keep a copy of the norms (+ error norms)
+                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qnorm2.p, h->qnorm.p, (size_t)cq * 8, cudaMemcpyDeviceToDevice, st));
                     KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, rescan.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
                     gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
                     KIRAG_LAUNCH_OK("gather_rows_kernel");
                     std::vector<int> still_bad;
-                    if (rescan_search(h, h->qsel.as<float>(), h->qnorm2.as<float>(), nb, k, Dd, Id, h->qmap.as<int>(),
+                    if (rescan_search(h, h->qsel.as<float>(), h->qnorm2.as<float>(), h->qnorm2.as<float>() + cq, nb, k, Dd, Id,
+                                      h->qmap.as<int>(),
                                       id_offset, kSelectSeg, &still_bad, st)) return 1;
                     for (int i : still_bad) exact.push_back(rescan[(size_t)i]);
                     n_rescan += nb - (int64_t)still_bad.size();
@@ -731,7 +753,7 @@ int kirag_index_create(int d, int metric, int device, kirag_index_t** out) {
     h->metric = metric;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
-    if (cudaMalloc((void**)&h->maxnorm2_bits, 4) != cudaSuccess || cudaMemset(h->maxnorm2_bits, 0, 4) != cudaSuccess) {
+    if (cudaMalloc((void**)&h->maxnorm2_bits, 8) != cudaSuccess || cudaMemset(h->maxnorm2_bits, 0, 8) != cudaSuccess) {
         set_error("index_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete h;
         return 1;
@@ -776,13 +798,14 @@ int kirag_index_add(kirag_index_t* h, const float* x, int64_t n, int x_is_device
     float* dst = h->master + h->ntotal * (int64_t)h->d;
     KIRAG_CUDA_OK(cudaMemcpyAsync(dst, x, (size_t)n * h->d * sizeof(float),
                                   x_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    if (launch_convert_rows(dst, n, h->d, h->ntotal, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, st)) return 1;
-    unsigned bits = 0;
-    KIRAG_CUDA_OK(cudaMemcpyAsync(&bits, h->maxnorm2_bits, 4, cudaMemcpyDeviceToHost, st));
+    if (launch_convert_rows(dst, n, h->d, h->ntotal, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, nullptr, st)) return 1;
+    unsigned bits[2] = {0, 0};
+    KIRAG_CUDA_OK(cudaMemcpyAsync(bits, h->maxnorm2_bits, 8, cudaMemcpyDeviceToHost, st));
     KIRAG_CUDA_OK(cudaStreamSynchronize(st));
-    float m2;
-    memcpy(&m2, &bits, 4);
-    h->maxnorm = sqrtf(m2);
+    float m2[2];
+    memcpy(m2, bits, 8);
+    h->maxnorm = sqrtf(m2[0]);
+    h->maxerr = h->shadow ? sqrtf(m2[1]) : 0.f;
     h->ntotal += n;
     return 0;
 }
@@ -852,7 +875,7 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
         if (cudaMemsetAsync(cnt.p, 0, (size_t)nq_pad * 4, st) != cudaSuccess) break;
         if (cudaMemsetAsync(dump.p, 0, (size_t)h->ntotal * nq * 4, st) != cudaSuccess) break;
         if (fill_f32(tau.as<float>(), INFINITY, nq_pad, st)) break;
-        if (launch_convert_rows(qd.as<float>(), nq, d, 0, qs.p, plan.q_tile_rows, nullptr, nullptr, st)) break;
+        if (launch_convert_rows(qd.as<float>(), nq, d, 0, qs.p, plan.q_tile_rows, nullptr, nullptr, nullptr, st)) break;
         if (launch_scan_tc_dump(h->shadow, h->ntotal, d, qs.p, nq, plan, tau.as<float>(), cnt.as<int>(),
                                 dump.as<float>(), nq, h->num_sms, st)) break;
         if (cudaMemcpyAsync(out_host, dump.p, (size_t)h->ntotal * nq * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||

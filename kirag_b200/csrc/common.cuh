@@ -191,7 +191,7 @@ __device__ __forceinline__ float warp_butterfly_sum(float v) {
 // ------------------------------------------------------ kernel launchers ---
 // convert.cu
 int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row0, void* shadow,
-                        int rows_per_tile, unsigned* maxnorm2_bits, float* row_norms,
+                        int rows_per_tile, unsigned* maxnorm2_bits, float* row_norms, float* row_errs,
                         cudaStream_t st);
 // scan_exact.cu
 constexpr int kExactNQ = 4;
@@ -212,7 +212,7 @@ int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, in
                         cudaStream_t st);
 int launch_final(const Cand* cand, int64_t cand_stride, const float* rescored, const int* cnt,
                  int fixed_count, int m_in, int nq, int k, float* D, int64_t* I, int64_t id_offset,
-                 const float* tau, const float* qnorm, float eps_factor, int check_cert,
+                 const float* tau, const float* qnorm, const float* qerr, float eps_a, float eps_b, int check_cert,
                  const int* overflow, int* flags, const int* qmap, cudaStream_t st);
 int launch_merge(const float* D_all, const int64_t* I_all, int G, int64_t nq, int k, float* D_out,
                  int64_t* I_out, cudaStream_t st);

@@ -16,7 +16,8 @@ namespace kirag {
 __global__ void __launch_bounds__(256)
 convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_t dst_row0,
                     uint8_t* __restrict__ shadow, int rows_per_tile,
-                    unsigned* __restrict__ maxnorm2_bits, float* __restrict__ row_norms) {
+                    unsigned* __restrict__ maxnorm2_bits, float* __restrict__ row_norms,
+                    float* __restrict__ row_errs) {
     pdl_wait();
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
@@ -26,6 +27,7 @@ convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_
     for (int64_t r = warp; r < n_rows; r += n_warps) {
         const float* row = src + r * (int64_t)d;
         float ss = 0.0f;
+        float es = 0.0f;  // squared norm of the bf16 rounding error of this row (exact differences, fp32 sum)
         for (int g = lane; g < n_gran; g += 32) {
             const float4 a = *reinterpret_cast<const float4*>(row + g * 8);
             const float4 b = *reinterpret_cast<const float4*>(row + g * 8 + 4);
@@ -37,6 +39,15 @@ convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_
             __nv_bfloat162 p1 = __floats2bfloat162_rn(a.z, a.w);
             __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y);
             __nv_bfloat162 p3 = __floats2bfloat162_rn(b.z, b.w);
+            {
+                const float2 r0 = __bfloat1622float2(p0), r1 = __bfloat1622float2(p1);
+                const float2 r2 = __bfloat1622float2(p2), r3 = __bfloat1622float2(p3);
+                float e;
+                e = a.x - r0.x; es = fmaf(e, e, es); e = a.y - r0.y; es = fmaf(e, e, es);
+                e = a.z - r1.x; es = fmaf(e, e, es); e = a.w - r1.y; es = fmaf(e, e, es);
+                e = b.x - r2.x; es = fmaf(e, e, es); e = b.y - r2.y; es = fmaf(e, e, es);
+                e = b.z - r3.x; es = fmaf(e, e, es); e = b.w - r3.y; es = fmaf(e, e, es);
+            }
             uint4 o;
             o.x = *reinterpret_cast<uint32_t*>(&p0);
             o.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -46,13 +57,18 @@ convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_
             *reinterpret_cast<uint4*>(shadow + off) = o;
         }
         ss = warp_butterfly_sum(ss);
+        es = warp_butterfly_sum(es);
         if (lane == 0) {
             if (row_norms) row_norms[r] = sqrtf(ss);
+            if (row_errs) row_errs[r] = (es == es) ? sqrtf(es) : INFINITY;
             // non-negative floats order like their bit patterns; NaN/inf norms
-            // saturate the bound (certificate then always fails -> exact path)
+            // saturate the bound (certificate then always fails -> exact path).
+            // [0] = max ||x||^2, [1] = max ||x - bf16(x)||^2
             if (maxnorm2_bits) {
                 unsigned bits = (ss == ss) ? __float_as_uint(ss) : 0x7f800000u;
                 atomicMax(maxnorm2_bits, bits);
+                unsigned ebits = (es == es) ? __float_as_uint(es) : 0x7f800000u;
+                atomicMax(maxnorm2_bits + 1, ebits);
             }
         }
     }
@@ -81,7 +97,7 @@ row_norms_kernel(const float* __restrict__ src, int64_t n_rows, int d,
 }
 
 int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row0, void* shadow,
-                        int rows_per_tile, unsigned* maxnorm2_bits, float* row_norms,
+                        int rows_per_tile, unsigned* maxnorm2_bits, float* row_norms, float* row_errs,
                         cudaStream_t st) {
     if (n_rows <= 0) return 0;
     const int threads = 256;
@@ -91,7 +107,7 @@ int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row
     if (shadow) {
         KIRAG_CHECK(d % 64 == 0, "convert: d=%d is not a multiple of 64", d);
         KIRAG_CUDA_OK(launch_chained(convert_rows_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, src, n_rows, d,
-                                     dst_row0, (uint8_t*)shadow, rows_per_tile, maxnorm2_bits, row_norms));
+                                     dst_row0, (uint8_t*)shadow, rows_per_tile, maxnorm2_bits, row_norms, row_errs));
         KIRAG_LAUNCH_OK("convert_rows_kernel");
     } else {
         row_norms_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, n_rows, d, maxnorm2_bits,

@@ -335,14 +335,15 @@ compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cn
 // grid nq.  Sorts the (canonical fp32 score, row) pairs, writes the first k as
 // the result row and checks the exactness certificate:
 //   every row that is NOT a candidate has approximate score <= tau[q]; its
-//   canonical score is therefore <= tau[q] + eps with eps = eps_factor *
-//   ||q|| (eps_factor already contains max_j ||x_j||).  If the k-th canonical
+//   canonical score is therefore <= tau[q] + eps with eps = eps_a * ||q|| +
+//   eps_b * ||q - bf16(q)|| (api.cu::CertEps: the corpus-side maxima are folded
+//   into eps_a / eps_b).  If the k-th canonical
 //   score exceeds tau[q] + eps, no dropped row can enter the top-k.
 __global__ void __launch_bounds__(1024)
 final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __restrict__ rescored,
              const int* __restrict__ cnt, int fixed_count, int m_in, int k, float* __restrict__ D,
              int64_t* __restrict__ I, int64_t id_offset, const float* __restrict__ tau,
-             const float* __restrict__ qnorm, float eps_factor, int check_cert,
+             const float* __restrict__ qnorm, const float* __restrict__ qerr, float eps_a, float eps_b, int check_cert,
              const int* __restrict__ overflow, int* __restrict__ flags,
              const int* __restrict__ qmap) {
     extern __shared__ uint64_t items[];
@@ -387,7 +388,7 @@ final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __
                     fail = 1;
                 } else {
                     const float kth = key_score(item_key(items[k - 1]));
-                    const float eps = eps_factor * qnorm[q];
+                    const float eps = eps_a * qnorm[q] + eps_b * qerr[q];
                     if (!(kth - eps > t)) fail = 1;
                 }
             }
@@ -525,14 +526,14 @@ int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, in
 
 int launch_final(const Cand* cand, int64_t cand_stride, const float* rescored, const int* cnt,
                  int fixed_count, int m_in, int nq, int k, float* D, int64_t* I, int64_t id_offset,
-                 const float* tau, const float* qnorm, float eps_factor, int check_cert,
+                 const float* tau, const float* qnorm, const float* qerr, float eps_a, float eps_b, int check_cert,
                  const int* overflow, int* flags, const int* qmap, cudaStream_t st) {
     KIRAG_CHECK(m_in <= kSelectSeg, "final: m_in=%d > %d", m_in, kSelectSeg);
     const int P = host_pow2(m_in);
     const size_t smem = (size_t)P * 8;
     if (ensure_smem(final_kernel, (size_t)kSelectSeg * 8)) return 1;
     KIRAG_CUDA_OK(launch_chained(final_kernel, dim3((unsigned)nq), dim3(sort_threads(P)), smem, st, cand, cand_stride,
-                                 rescored, cnt, fixed_count, m_in, k, D, I, id_offset, tau, qnorm, eps_factor, check_cert,
+                                 rescored, cnt, fixed_count, m_in, k, D, I, id_offset, tau, qnorm, qerr, eps_a, eps_b, check_cert,
                                  overflow, flags, qmap));
     KIRAG_LAUNCH_OK("final_kernel");
     return 0;
