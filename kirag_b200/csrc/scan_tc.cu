@@ -218,7 +218,6 @@ struct ScanArgs {
     int cap;
     int n_stages;
     int x_policy;      // L2 policy of corpus blocks that are re-read per query tile: 1 normal, 2 evict_last
-    int tau_ldg;       // experiment switch (KIRAG_TAU_LDG=1): read tau through L1 instead of L2
     int q_dep;         // 1: the query shadow is written by the kernel right before this one in the chain
                        // (level 0): the producer must pdl_wait() too; 0: only the filter warps wait
     float* dump;       // optional [n_rows, dump_ld] dense approx scores (debug / tests)
@@ -252,7 +251,7 @@ __device__ __forceinline__ uint32_t pass_mask(const ScanArgs& a, const uint32_t 
         const float4* tp = reinterpret_cast<const float4*>(a.tau + q0);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 t = a.tau_ldg ? __ldg(tp + c4) : __ldcg(tp + c4);
+            const float4 t = __ldcg(tp + c4);
             pass |= (__uint_as_float(v[c4 * 4 + 0]) >= t.x ? 1u : 0u) << (c4 * 4 + 0);
             pass |= (__uint_as_float(v[c4 * 4 + 1]) >= t.y ? 1u : 0u) << (c4 * 4 + 1);
             pass |= (__uint_as_float(v[c4 * 4 + 2]) >= t.z ? 1u : 0u) << (c4 * 4 + 2);
@@ -885,7 +884,6 @@ int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshado
                    int q_dep, cudaStream_t st) {
     ScanArgs args{};
     args.q_dep = q_dep;
-    args.tau_ldg = env_flag("KIRAG_TAU_LDG", 0);
     args.shadow = (const uint8_t*)shadow;
     args.qshadow = (const uint8_t*)qshadow;
     args.n_rows = n_rows;

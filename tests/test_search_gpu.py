@@ -152,6 +152,23 @@ def test_auto_path_unit_vectors_uses_the_filter(fa, n, d, nq, k):
     assert np.array_equal(I, Ie) and np.array_equal(D, De), f"fast vs exact differ (near-tie swaps vs fp64: {n_swaps})"
 
 
+@pytest.mark.parametrize("n,nq,k", [(20000, 8, 10), (70000, 64, 10), (70000, 129, 10), (300000, 4, 100), (300000, 300, 100)])
+def test_levels_follow_the_host_schedule(fa, n, nq, k):
+    """The number of filter launches of a search equals the host-side schedule hook (tests/test_host_logic.py
+    checks that hook's invariants on CPU)."""
+    import ctypes
+
+    from kirag_b200 import _lib
+
+    rng = np.random.default_rng(n + nq)
+    xb, xq = unit_rows(rng, n, 128), unit_rows(rng, nq, 128)
+    D, I, st = build(fa, xb).search_ex(xq, k, path=AUTO)
+    out = (ctypes.c_int64 * 64)()
+    n_levels = _lib.load().kirag_debug_level_schedule(n, nq, k, 128, out, 64, None, None)
+    assert st["levels"] == n_levels and out[n_levels - 1] == n, (st, n_levels)
+    assert_topk_parity(D, I, xb, xq, k, what=f"schedule {st}")
+
+
 def test_fast_path_without_escalation_reports_certificate(fa):
     rng = np.random.default_rng(5)
     xb, xq = unit_rows(rng, 50000, 128), unit_rows(rng, 12, 128)
