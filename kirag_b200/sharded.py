@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import warnings
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -59,6 +60,10 @@ def merge_topk_device(D_all: torch.Tensor, I_all: torch.Tensor) -> Tuple[torch.T
     return D, I
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """CUDA IPC mapping of a peer's exchange buffer failed on at least one rank (raised on EVERY rank)."""
+
+
 class PeerExchange:
     """This rank's exchange buffer + the IPC mappings of every peer's (kirag_exchange_* C ABI).
 
@@ -83,8 +88,18 @@ class PeerExchange:
             dist.all_gather_object(handles, bytes(mine.raw), group=group)
             blob = b"".join(handles)
             assert len(blob) == nb * self.world_size
-            _lib.check(self._lib.kirag_exchange_connect(self._h, blob), "exchange_connect")
-            dist.barrier(group=group)  # nobody pushes before every rank has mapped every buffer
+            # mapping a peer's buffer fails where the peer GPU is not visible / not P2P-reachable from this
+            # process; every rank has to reach the same verdict, so the outcome is agreed on before anyone
+            # raises (a half-connected group would dead-lock in the first exchange)
+            status = self._lib.kirag_exchange_connect(self._h, blob)
+            err = _lib.last_error() if status else ""
+            outcomes = [None] * self.world_size
+            dist.all_gather_object(outcomes, (int(status), err), group=group)  # also the "everyone has mapped" barrier
+            bad = [(r, e) for r, (st, e) in enumerate(outcomes) if st]
+            if bad:
+                self.close()
+                raise PeerExchangeUnavailable("peer-memory exchange could not be set up: " +
+                                              "; ".join(f"rank {r}: {e}" for r, e in bad))
 
     def fits(self, nq: int, k: int) -> bool:
         return 0 < k <= self.max_k and nq * k <= self.max_nq * self.max_k
@@ -144,7 +159,14 @@ class ShardedFlatIP:
         assert self.exchange in ("peer", "nccl"), f"unknown exchange {self.exchange!r}"
         self.peer: Optional[PeerExchange] = None
         if self.exchange == "peer" and self.world_size > 1:
-            self.peer = PeerExchange(self.index.device, self.rank, self.world_size, max_nq, max_k, group=group)
+            try:
+                self.peer = PeerExchange(self.index.device, self.rank, self.world_size, max_nq, max_k, group=group)
+            except PeerExchangeUnavailable as exc:
+                if exchange == "peer" or os.environ.get("KIRAG_EXCHANGE") == "peer":
+                    raise  # explicitly requested
+                # every rank raised together: all of them fall back to the collective path
+                warnings.warn(f"kirag_b200.sharded: {exc}; using the NCCL all-gather + merge path instead")
+                self.exchange = "nccl"
 
     @property
     def ntotal_local(self) -> int:
