@@ -11,9 +11,10 @@
 //   wait   : CTA b polls its OWN flags[g][b] (acquire, system scope) until all G ranks have
 //            delivered that query range — there is no grid-wide or GPU-wide barrier, a query
 //            range is merged as soon as its G pieces are there;
-//   merge  : the G lists are sorted by (score desc, id asc) and hold distinct ids, so the global
-//            rank of an item is the number of items that precede it in each list: G binary
-//            searches per item, no sort, no barrier.  Items of rank < k are written out.
+//   merge  : the G lists are sorted by (score desc, id asc) and hold distinct ids, so two lists are
+//            merged by ranking: position in the own list + binary-search rank in the other one.
+//            A pairwise tree (log2 G rounds, truncated to k after every round) merges the G lists
+//            of a query; four queries are in flight per CTA.  No sort.
 // Buffers are double-buffered by epoch parity: a rank can be at most one call ahead of its peers
 // (it cannot finish call e before every peer has STARTED call e, i.e. finished call e-1), so
 // data of call e+1 never lands in a slot that call e-1 is still reading.
@@ -48,6 +49,7 @@ struct ExchangeArgs {
     int64_t* I_out;
     int vec16;     // rows can be copied with 16-byte accesses (k % 4 == 0, aligned bases)
     int n_groups;  // thread groups per CTA in the merge phase (1, 2 or 4), one query each at a time
+    int tree;      // 1: pairwise merge tree (needs two list buffers in shared memory), 0: rank-everything merge
 };
 
 __device__ __forceinline__ uint8_t* slot_ptr(const ExchangeArgs& a, int dst, int src) {
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
     extern __shared__ uint64_t xsmem[];
     const int G = a.G, k = a.k;
     const int L = G * k;
-    __shared__ int n_valid_all[4][kMaxRanks];
+    __shared__ int n_valid_all[4][2 * kMaxRanks];
     const int b = blockIdx.x, NB = gridDim.x;
     const int64_t q_lo = a.nq * b / NB, q_hi = a.nq * (b + 1) / NB;
     const int64_t e_lo = q_lo * k, e_hi = q_hi * k;
@@ -149,9 +151,70 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
     const int gthreads = kExchangeThreads / n_groups;
     const int grp = threadIdx.x / gthreads;
     const int gt = threadIdx.x - grp * gthreads;
+    int* n_valid = n_valid_all[grp];
+    if (a.tree) {
+        // Pairwise merge tree (log2 G rounds): two sorted lists are merged by giving every element the rank
+        // "own position + number of elements of the sibling list that precede it" (one binary search) and
+        // keeping ranks < k — the top-k of a union is in the union of the top-k's, so truncating after
+        // every round is exact.  O(G k log k) steps per query instead of O(G^2 k log k).
+        int64_t* ids_buf = reinterpret_cast<int64_t*>(xsmem) + (size_t)grp * 2 * L;                               // [2][L]
+        uint32_t* keys_buf = reinterpret_cast<uint32_t*>(reinterpret_cast<int64_t*>(xsmem) + (size_t)n_groups * 2 * L) +
+                             (size_t)grp * 2 * L;                                                                    // [2][L]
+        int* nv[2] = {n_valid, n_valid + kMaxRanks};
+        for (int64_t q = q_lo + grp; q < q_hi; q += n_groups) {
+            if (gt < G) nv[0][gt] = 0;
+            group_barrier(1 + grp, gthreads);
+            for (int i = gt; i < L; i += gthreads) {
+                const int g = i / k, j = i - g * k;
+                const uint8_t* slot = slot_ptr(a, a.rank, g);
+                const int64_t id = __ldcg(reinterpret_cast<const int64_t*>(slot + a.ids_off) + q * k + j);
+                uint32_t key = 0u;
+                if (id >= 0) key = score_key(__ldcg(reinterpret_cast<const float*>(slot) + q * k + j));
+                keys_buf[i] = key;
+                ids_buf[i] = id;
+                if (key != 0u) atomicAdd(&nv[0][g], 1);  // valid items form a prefix of each list
+            }
+            group_barrier(1 + grp, gthreads);
+            int cur = 0;
+            for (int n_lists = G; n_lists > 1; n_lists = (n_lists + 1) >> 1) {
+                const uint32_t* kin = keys_buf + (size_t)cur * L;
+                const int64_t* iin = ids_buf + (size_t)cur * L;
+                uint32_t* kout = keys_buf + (size_t)(cur ^ 1) * L;
+                int64_t* iout = ids_buf + (size_t)(cur ^ 1) * L;
+                const int* nin = nv[cur];
+                int* nout = nv[cur ^ 1];
+                for (int i = gt; i < n_lists * k; i += gthreads) {
+                    const int l = i / k, j = i - l * k;
+                    const int mate = l ^ 1;
+                    const int n_own = nin[l];
+                    const int n_mate = (mate < n_lists) ? nin[mate] : 0;
+                    if (j == 0 && (l & 1) == 0) nout[l >> 1] = (n_own + n_mate < k) ? (n_own + n_mate) : k;
+                    if (j >= n_own) continue;
+                    const uint32_t key = kin[i];
+                    const int64_t id = iin[i];
+                    const int r = j + (n_mate ? count_before(kin + mate * k, iin + mate * k, n_mate, key, id) : 0);
+                    if (r < k) {
+                        kout[(l >> 1) * k + r] = key;
+                        iout[(l >> 1) * k + r] = id;
+                    }
+                }
+                group_barrier(1 + grp, gthreads);
+                cur ^= 1;
+            }
+            const int total = nv[cur][0];
+            for (int j = gt; j < k; j += gthreads) {
+                const bool ok = j < total;
+                a.D_out[q * k + j] = ok ? key_score(keys_buf[(size_t)cur * L + j]) : -FLT_MAX;
+                a.I_out[q * k + j] = ok ? ids_buf[(size_t)cur * L + j] : -1;
+            }
+            group_barrier(1 + grp, gthreads);
+        }
+        return;
+    }
+    // rank-everything merge (lists too long for two shared-memory buffers): an item's global rank is the sum
+    // of its binary-search ranks in the other lists
     int64_t* ids = reinterpret_cast<int64_t*>(xsmem) + (size_t)grp * L;                        // [L]
     uint32_t* keys = reinterpret_cast<uint32_t*>(reinterpret_cast<int64_t*>(xsmem) + (size_t)n_groups * L) + (size_t)grp * L;  // [L]
-    int* n_valid = n_valid_all[grp];
     for (int64_t q = q_lo + grp; q < q_hi; q += n_groups) {
         if (gt < G) n_valid[gt] = 0;
         group_barrier(1 + grp, gthreads);
@@ -359,7 +422,9 @@ int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int
     a.I_out = I_out;
     // the grid must be the same on every rank (flags are per block): derived from nq only
     int blocks = (int)(nq < kExchangeMaxBlocks ? nq : kExchangeMaxBlocks);
-    const size_t per_query = (size_t)x->world * k * 12;
+    const size_t list_bytes = (size_t)x->world * k * 12;
+    a.tree = (2 * list_bytes <= 96 * 1024) ? 1 : 0;  // two buffers of G*k (key, id) pairs per merge group
+    const size_t per_query = a.tree ? 2 * list_bytes : list_bytes;
     int n_groups = 4;
     while (n_groups > 1 && per_query * n_groups > 96 * 1024) n_groups >>= 1;
     a.n_groups = n_groups;
