@@ -401,6 +401,7 @@ def run_ours(args):
         }
         emit(line)
     if dist_ok:
+        sh.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -410,9 +410,12 @@ int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int
     a.G = x->world;
     a.nq = nq;
     a.k = k;
-    x->epoch += 1;
+    // the epoch only has to differ from the values two calls back; it is advanced in unsigned arithmetic
+    // so that a long-running server wraps around instead of overflowing a signed int
+    x->epoch = (int)((unsigned)x->epoch + 1u);
+    if (x->epoch == 0) x->epoch = (int)2u;  // 0 is the "never written" flag value; keep the parity sequence (… 0xffffffff odd, 2 even)
     a.epoch = x->epoch;
-    a.parity = x->epoch & 1;
+    a.parity = (int)((unsigned)x->epoch & 1u);
     a.slot_bytes = x->slot_bytes;
     a.flags_off = x->flags_off;
     a.ids_off = align_up((size_t)nq * k * 4, 16);

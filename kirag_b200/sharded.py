@@ -168,6 +168,17 @@ class ShardedFlatIP:
                 warnings.warn(f"kirag_b200.sharded: {exc}; using the NCCL all-gather + merge path instead")
                 self.exchange = "nccl"
 
+    def close(self) -> None:
+        """Collective teardown of the peer mappings: nobody unmaps or frees a buffer a peer may still be
+        writing to.  Call it on every rank before destroying the process group (optional: process exit
+        cleans up as well)."""
+        if self.peer is not None:
+            torch.cuda.synchronize(self.index.device)
+            dist.barrier(group=self.group)
+            self.peer.close()
+            self.peer = None
+            dist.barrier(group=self.group)
+
     @property
     def ntotal_local(self) -> int:
         return int(self.index.ntotal)

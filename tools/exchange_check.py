@@ -67,6 +67,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
                 print(f"    exchange {name}: {t.item() * 1e3:8.1f} us (max over {world} ranks)", flush=True)
+    peer.close()
     dist.barrier()
     if rank == 0:
         print("exchange_check ok" if ok else "exchange_check FAILED", flush=True)
