@@ -161,6 +161,9 @@ __device__ __forceinline__ float canonical_partial(const float* __restrict__ x,
                                                    bool vec4) {
     float acc = 0.0f;
     if (vec4) {
+        // unrolled so that the independent loads of a row are in flight together; the FMA chain (and with
+        // it the summation order) is the same sequential one
+#pragma unroll 8
         for (int c = lane * 4; c < d; c += 128) {
             const float4 xv = *reinterpret_cast<const float4*>(x + c);
             const float4 qv = *reinterpret_cast<const float4*>(q + c);
