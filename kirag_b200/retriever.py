@@ -92,11 +92,10 @@ class DeviceDenseRetriever(torch.nn.Module):
         ids = id_map[I].astype(str).tolist()  # -1 padding maps to the last id, as in retriever/index.py:49
         return ids, D
 
-    def batch_retrieve(self, queries: List[str], topk: int, verbose: bool = False, **kwargs) -> List[dict]:
-        emb = self.calculate_query_embeddings(queries=queries, verbose=verbose, **kwargs)
-        ids, scores = self.search_embeddings(emb, topk)
+    def parse_indexer_output(self, indexer_output) -> List[List[dict]]:
+        """Same contract as retrievers.py:234-248: [(ids, scores), ...] -> [[document dict + "score", ...], ...]."""
         retrieval_results = []
-        for topk_str_indices, topk_score_array in zip(ids, scores):
+        for topk_str_indices, topk_score_array in indexer_output:
             one = []
             for docid, score in zip(topk_str_indices, topk_score_array):
                 if self.corpus is not None:
@@ -107,6 +106,11 @@ class DeviceDenseRetriever(torch.nn.Module):
                 one.append(document)
             retrieval_results.append(one)
         return retrieval_results
+
+    def batch_retrieve(self, queries: List[str], topk: int, verbose: bool = False, **kwargs) -> List[dict]:
+        emb = self.calculate_query_embeddings(queries=queries, verbose=verbose, **kwargs)
+        ids, scores = self.search_embeddings(emb, topk)
+        return self.parse_indexer_output(zip(ids, scores))
 
     def forward(self, queries: Union[str, List[str]], topk: int, verbose: bool = False, **kwargs):
         assert self.indexer is not None  # must provide indexer
