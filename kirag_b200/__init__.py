@@ -11,7 +11,7 @@ the pooling op loads `libkirag_b200.so` and fails loudly if it is missing.
 """
 from . import _lib  # noqa: F401
 from .faiss_api import IndexFlatIP, read_index, write_index  # noqa: F401
-from .index import Indexer  # noqa: F401
+from .index import Indexer, ShardedIndexer  # noqa: F401
 
-__all__ = ["IndexFlatIP", "Indexer", "read_index", "write_index"]
+__all__ = ["IndexFlatIP", "Indexer", "ShardedIndexer", "read_index", "write_index"]
 __version__ = "0.1.0"

@@ -198,10 +198,17 @@ class ShardedFlatIP:
     def search(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """q [nq, d] replicated on every rank -> (D [nq,k], I [nq,k]) global result on every rank."""
         D_loc, I_loc = self.search_local(q, k)
+        return self.exchange_merge(D_loc, I_loc)
+
+    def exchange_merge(self, D_loc: torch.Tensor, I_loc: torch.Tensor,
+                       lists_sorted: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Per-rank results [nq,k] with globally unique ids (padding id -1) -> the global top-k on every rank.
+        `lists_sorted`: every row is ordered by (score desc, id asc) — what the peer kernel's sort-free merge
+        relies on; pass False (same value on every rank) to take the collective path, whose merge kernel sorts."""
         if self.world_size == 1:
             return D_loc, I_loc
-        nq = q.shape[0]
-        if self.peer is not None and self.peer.fits(nq, k):
+        nq, k = D_loc.shape
+        if lists_sorted and self.peer is not None and self.peer.fits(nq, k):
             return self.peer.merge(D_loc, I_loc)
         # ONE collective for scores and ids: the payload is tiny (12*nq*k bytes per rank), so the
         # exchange is latency-bound and a second all-gather would double its cost.  Scores ride in

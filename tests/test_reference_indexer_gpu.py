@@ -84,3 +84,33 @@ def test_reference_indexer_unmodified_on_the_b200_library(tmp_path):
         sys.path.remove(REFERENCE)
         sys.modules.pop("retriever.index", None)
         sys.modules.pop("faiss", None)
+
+
+def test_sharded_indexer_single_rank_equals_indexer(tmp_path):
+    """ShardedIndexer with one rank (no exchange): device-side row -> passage-id mapping, padding, serialise round
+    trip; the two-rank plumbing is covered by tests/test_sharded_gloo.py and the exchange by tests/test_exchange_gpu.py."""
+    from kirag_b200 import Indexer
+    from kirag_b200.index import ShardedIndexer
+
+    rng = np.random.default_rng(3)
+    xb, xq = unit_rows(rng, 30000, 256), unit_rows(rng, 70, 256)
+    ids = [str(7 * i + 1) for i in range(30000)]
+    ref = Indexer(256, "inner_product")
+    sh = ShardedIndexer(256, rank=0, world_size=1)
+    for a, b in ((0, 12000), (12000, 12001), (12001, 30000)):
+        ref.index_data(ids[a:b], xb[a:b])
+        sh.index_data(ids[a:b], xb[a:b])
+    want = ref.search_knn(xq, 20, index_batch_size=32, verbose=False)
+    got = sh.search_knn(xq, 20, index_batch_size=32, verbose=False)
+    assert len(got) == len(want) == 70
+    for (gi, gs), (wi, ws) in zip(got, want):
+        assert gi == wi and np.array_equal(gs, ws)
+    sh.serialize(str(tmp_path))
+    sh2 = ShardedIndexer(256, rank=0, world_size=1)
+    sh2.deserialize_from(str(tmp_path))
+    assert [r[0] for r in sh2.search_knn(xq[:8], 20, verbose=False)] == [r[0] for r in want[:8]]
+    # more results requested than rows: padding ids stay "-1"
+    tiny = ShardedIndexer(256, rank=0, world_size=1)
+    tiny.index_data(ids[:3], xb[:3])
+    (pi, ps), = tiny.search_knn(xq[:1], 5, verbose=False)
+    assert pi[3:] == ["-1", "-1"] and np.all(ps[3:] == np.float32(-3.4028234663852886e38))

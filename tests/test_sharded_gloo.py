@@ -65,3 +65,43 @@ def test_sharded_search_world_size_2(n, k):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, port, n, 16, 4, k, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+# ---------------------------------------------------------------- ShardedIndexer ---
+def _indexer_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kirag_b200.index import ShardedIndexer
+
+        rng = np.random.default_rng(21)
+        d, k = 16, 6
+        chunks = [(list(range(a, b)), int_corpus(rng, b - a, d)) for a, b in ((0, 40), (40, 45), (45, 120), (120, 121), (121, 200))]
+        xq = int_corpus(rng, 7, d)
+        ix = ShardedIndexer(d, local_index=_LocalOracleIndex(d), merge_fn=_merge)
+        for ids, emb in chunks:
+            ix.index_data([str(i) for i in ids], emb)  # ids arrive as strings, like the reference's passage ids
+        got = ix.search_knn(xq, k, index_batch_size=4)
+        xb = np.concatenate([e for _, e in chunks])
+        D1, I1 = oracle.flat_ip_search(xb, xq, k)
+        ok = len(got) == 7 and ix.ntotal_global == 200
+        for (ids, scores), d_ref, i_ref in zip(got, D1, I1):
+            ok = ok and ids == [str(i) for i in i_ref] and np.array_equal(scores, d_ref)
+        # every chunk lives on exactly one rank
+        ok = ok and ix.index.ntotal == sum(len(ids) for c, (ids, _) in enumerate(chunks) if c % world == rank)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_indexer_world_size_2_matches_single_index():
+    """SPMD `Indexer` over two ranks (chunks dealt round-robin, passage ids mapped before the merge) returns what
+    one flat index over all rows returns: same ids (as str), same scores, same (score desc, id asc) order."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_indexer_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
