@@ -19,6 +19,9 @@
  *   - inputs are borrowed for the duration of the call; outputs are
  *     caller-owned buffers.  The index owns its copy of the corpus (FAISS
  *     copies on add(), reference call site retriever/index.py:32).
+ *   - threading: calls on DIFFERENT index handles may run concurrently from different host threads;
+ *     calls on the SAME handle must be serialised by the caller (search workspaces belong to the
+ *     handle).  KiRAG's callers are single-threaded Python (retriever/retrievers.py:250-275).
  *   - there is NO CPU fallback.  If no CUDA device is usable every call fails
  *     with a non-zero status.
  */
