@@ -308,6 +308,35 @@ def measure_batch(sh, lib, q_all, batch, k, steps, warmup, device, dist_ok, peak
             "stats": stats_box.get("stats", {})}
 
 
+def parity_check(sh, q_all, batch, k, device, dist_ok, n_sample):
+    """Outside every timed region: the certified filter path (KIRAG_PATH_AUTO, what was timed) against the exact
+    fp32 CUDA-core scan (KIRAG_PATH_EXACT) on `n_sample` queries spread over the batch — ids and scores must be
+    bit-equal — plus the row-order / id-range properties on the whole batch.  For N > 1 both sides go through the
+    exchange+merge, and every rank must agree (MIN over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    from kirag_b200 import _lib
+
+    q = q_all[:batch].contiguous()
+    D, I = sh.search(q, k)
+    n_sample = min(n_sample, batch)
+    idx = torch.unique(torch.linspace(0, batch - 1, n_sample, device=device).round().long())
+    De, Ie = sh.search(q[idx].contiguous(), k, path=_lib.PATH_EXACT)
+    torch.cuda.synchronize(device)
+    mism = int((I[idx] != Ie).sum().item())
+    sdiff = float((D[idx] - De).abs().max().item())
+    ordered = bool((((D[:, :-1] > D[:, 1:]) | ((D[:, :-1] == D[:, 1:]) & (I[:, :-1] < I[:, 1:]))).all()).item())
+    in_range = bool(((I >= 0) & (I < sh.n_total)).all().item())
+    ok = mism == 0 and sdiff == 0.0 and ordered and in_range
+    if dist_ok:
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    return {"batch": batch, "ok": ok, "checked_queries": int(idx.numel()), "mismatched_ids": mism,
+            "max_abs_score_diff": sdiff, "rows_ordered": ordered, "ids_in_range": in_range}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -395,6 +424,17 @@ def run_ours(args):
                           "roofline_achieved": r["roofline"]["achieved"], "roofline_unit": r["roofline"]["unit"],
                           "n_fast": r["stats"].get("n_fast"), "n_exact": r["stats"].get("n_exact")})
 
+    # parity where the numbers are quoted (outside every timed region; every rank takes part for N > 1)
+    checks = [parity_check(sh, q_all, B, k, device, dist_ok, 64)]
+    for b in sweep:
+        if b != B:
+            checks.append(parity_check(sh, q_all, b, k, device, dist_ok, 16))
+    parity = {"ok": all(c["ok"] for c in checks), "checked_queries": sum(c["checked_queries"] for c in checks),
+              "method": "KIRAG_PATH_AUTO (timed path) vs KIRAG_PATH_EXACT (fp32 CUDA-core scan of the master) on sampled "
+                        "queries of every measured batch size: ids and scores bit-equal; all rows ordered by (score desc, "
+                        "id asc); for N > 1 both through the exchange+merge, MIN over ranks",
+              "per_batch": checks}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the CPU leg runs in its own process (own thread-pool settings), through the reference arm
@@ -428,6 +468,7 @@ def run_ours(args):
             "gpu_launches": (int(head["stats"].get("kernel_launches", 0)) + (1 if world > 1 else 0)) * args.steps,
             "clocks": clocks,
             "search_stats": head["stats"],
+            "parity": parity,
             "rank_diag": rank_diag,
             "sweep": sweep_out,
         }

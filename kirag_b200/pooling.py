@@ -121,18 +121,23 @@ def bge_embed(last_hidden_states: torch.Tensor) -> torch.Tensor:
     return pool_normalize(last_hidden_states, None, mode="cls", normalize=True)
 
 
-def patch_reference_encoders(encoders_module=None, e5_module=None) -> None:
-    """Substitute the fused epilogue into the reference's modules.
+def patch_reference_encoders(encoders_module=None, e5_module=None):
+    """Substitute the fused epilogue into the reference's modules; returns a callable that undoes it.
 
     `encoders_module` is the imported /root/reference/retriever/encoders.py,
     `e5_module` the imported retriever/e5.py.  E5Encoder / BGEEncoder keep their
-    HF BertModel body (out of scope) and get a forward whose tail is one kernel.
+    HF BertModel body (out of scope) and get a forward whose tail is one kernel
+    (encoders.py:67-77 and :106-118 otherwise unchanged: same arguments, same return).
     """
     from transformers import BertModel
 
-    if encoders_module is not None:
-        encoders_module.average_pool = average_pool
+    saved = []
 
+    def swap(obj, name, value):
+        saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    if encoders_module is not None:
         def e5_forward(self, input_ids, attention_mask, token_type_ids=None, **kwargs):
             out = BertModel.forward(self, input_ids=input_ids, attention_mask=attention_mask,
                                     token_type_ids=token_type_ids, return_dict=True)
@@ -143,7 +148,15 @@ def patch_reference_encoders(encoders_module=None, e5_module=None) -> None:
                                     token_type_ids=token_type_ids, return_dict=True)
             return bge_embed(out.last_hidden_state)
 
-        encoders_module.E5Encoder.forward = e5_forward
-        encoders_module.BGEEncoder.forward = bge_forward
+        swap(encoders_module, "average_pool", average_pool)
+        swap(encoders_module.E5Encoder, "forward", e5_forward)
+        swap(encoders_module.BGEEncoder, "forward", bge_forward)
     if e5_module is not None:
-        e5_module.average_pool = average_pool
+        swap(e5_module, "average_pool", average_pool)
+
+    def undo():
+        while saved:
+            obj, name, value = saved.pop()
+            setattr(obj, name, value)
+
+    return undo

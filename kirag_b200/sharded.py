@@ -191,13 +191,16 @@ class ShardedFlatIP:
             self.index.add(x_local.numpy() if isinstance(x_local, torch.Tensor) else x_local)
         assert self.index.ntotal <= self.hi - self.lo, "more rows added than this rank's shard holds"
 
-    def search_local(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Per-shard exact top-k with global ids."""
-        return self.index.search_device(q, k, id_offset=self.lo)
+    def search_local(self, q: torch.Tensor, k: int, path: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Per-shard exact top-k with global ids.  `path`: a KIRAG_PATH_* selector (default AUTO; EXACT = the fp32
+        CUDA-core scan, what bench.py's parity block and the large-config tests compare AUTO with)."""
+        if path is None:
+            return self.index.search_device(q, k, id_offset=self.lo)
+        return self.index.search_device(q, k, id_offset=self.lo, path=path)
 
-    def search(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    def search(self, q: torch.Tensor, k: int, path: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """q [nq, d] replicated on every rank -> (D [nq,k], I [nq,k]) global result on every rank."""
-        D_loc, I_loc = self.search_local(q, k)
+        D_loc, I_loc = self.search_local(q, k, path=path)
         return self.exchange_merge(D_loc, I_loc)
 
     def exchange_merge(self, D_loc: torch.Tensor, I_loc: torch.Tensor,

@@ -1,14 +1,12 @@
 """The Indexer interface end to end on the GPU: our mirror, and (when a copy of the reference file is
 present) the reference's own retriever/index.py running unmodified on kirag_b200.as_faiss."""
-import importlib
 import os
-import sys
 
 import numpy as np
 import pytest
 
 from oracle import oracle
-from tests.conftest import REFERENCE, unit_rows
+from tests.conftest import unit_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -64,26 +62,39 @@ def test_build_index_from_saved_embedding_shards(tmp_path):
 
 
 def test_reference_indexer_unmodified_on_the_b200_library(tmp_path):
-    if not os.path.isdir(os.path.join(REFERENCE, "retriever")):
-        pytest.skip("/root/reference is not present on this box")
-    import kirag_b200.as_faiss as af
+    """retriever/index.py from the sha256-verified snapshot baseline/_ref (the only copy of the reference that
+    exists on the GPU box), byte-for-byte unmodified, with `faiss` = kirag_b200.as_faiss."""
+    from tests import refenv
 
-    af.install()
-    sys.path.insert(0, REFERENCE)
-    sys.modules.pop("retriever.index", None)
-    try:
-        ref = importlib.import_module("retriever.index")
+    root = refenv.snapshot_root()
+    if root is None:
+        pytest.skip("baseline/_ref snapshot missing or stale: run __graft_entry__.build() in the build container")
+    import kirag_b200.as_faiss as af
+    from kirag_b200 import faiss_api
+
+    with refenv.reference_modules(root, af.make_module()) as ref:
         rng = np.random.default_rng(2)
-        xb, xq = unit_rows(rng, 5000, 1024), unit_rows(rng, 5, 1024)
-        ix = ref.Indexer(1024, "inner_product")
-        ix.index_data([str(i) for i in range(5000)], xb)
+        xb, xq = unit_rows(rng, 50000, 1024), unit_rows(rng, 1100, 1024)  # two faiss calls of <= 1024 queries
+        ix = ref.index.Indexer(1024, "inner_product")
+        assert isinstance(ix.index, faiss_api.IndexFlatIP)
+        ix.index_data([str(3 * i + 1) for i in range(20000)], xb[:20000])
+        ix.index_data([str(3 * i + 1) for i in range(20000, 50000)], xb[20000:])
         res = ix.search_knn(xq, 10, verbose=False)
-        Do, Io = oracle.flat_ip_search(xb, xq, 10, accum="f64")
-        assert [r[0] for r in res] == [[str(i) for i in row] for row in Io]
-    finally:
-        sys.path.remove(REFERENCE)
-        sys.modules.pop("retriever.index", None)
-        sys.modules.pop("faiss", None)
+        Do, Io = oracle.flat_ip_search_blas(xb, xq, 10, use_torch=True)
+        assert len(res) == 1100 and isinstance(res[0][0][0], str)
+        bad = sum(r[0] != [str(3 * i + 1) for i in row] for r, row in zip(res, Io))
+        assert bad <= 2  # fp32 near-tie swaps only
+        np.testing.assert_allclose(np.stack([r[1] for r in res]), Do, rtol=1e-5, atol=1e-6)
+        ix.serialize(str(tmp_path))
+        ix2 = ref.index.Indexer(1024, "inner_product")
+        ix2.deserialize_from(str(tmp_path))
+        res2 = ix2.search_knn(xq[:40], 10, verbose=False)
+        assert [r[0] for r in res2] == [r[0] for r in res[:40]]
+        # k > ntotal: FAISS padding (-1) indexes the LAST id in the reference's own mapping (index.py:49)
+        tiny = ref.index.Indexer(1024, "inner_product")
+        tiny.index_data(["7", "8", "9"], xb[:3])
+        (ids, scores), = tiny.search_knn(xq[:1], 5, verbose=False)
+        assert ids[3:] == ["9", "9"] and np.all(scores[3:] == np.float32(-3.4028234663852886e38))
 
 
 def test_sharded_indexer_single_rank_equals_indexer(tmp_path):
