@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KIRAG_ABI_VERSION 3
+#define KIRAG_ABI_VERSION 4
 
 /* metric ids; only inner product is implemented, as only inner product is
  * ever constructed by the reference (retrieve.py:112, faiss_index_corpus.py:29) */
@@ -129,10 +129,16 @@ int kirag_index_dim(const kirag_index_t* h);
  * (k > ntotal) hold D = -FLT_MAX (numeric_limits<float>::lowest()), I = -1,
  * which is FAISS's heap neutral element.  `id_offset` is added to every
  * returned id (row-sharded multi-GPU search: global id = local row + offset).
- * ptrs_are_device: 0 = q/D/I are host pointers (call is synchronous),
- *                  1 = device pointers on the index's device (stream-ordered;
- *                      the call may still synchronise internally when a query
- *                      has to be escalated to the exact path). */
+ * k <= 2048; the over-fetch of the filter path is k' = min(4k, 2048).
+ * ptrs_are_device: 0 = q/D/I are host pointers.  The call is synchronous like FAISS; results and the
+ *                      per-query certificate flags come back together, ONE stream synchronisation
+ *                      per 16384 queries (a second one only if a query had to be re-answered).
+ *                  1 = device pointers on the index's device.  The work is enqueued on `stream`, then
+ *                      the call synchronises ONCE (per 16384 queries) to read the certificate flags and
+ *                      re-answers flagged queries before returning: on return D/I are final, but the
+ *                      call is NOT purely stream-ordered.  Use kirag_index_search_async +
+ *                      kirag_index_search_finish where the synchronisation has to move (e.g. behind a
+ *                      collective) or where the call is captured into a CUDA graph. */
 int kirag_index_search(kirag_index_t* h, const float* q, int64_t nq, int k,
                        float* D, int64_t* I, int ptrs_are_device, int64_t id_offset, void* stream);
 
@@ -140,6 +146,28 @@ int kirag_index_search(kirag_index_t* h, const float* q, int64_t nq, int k,
 int kirag_index_search_ex(kirag_index_t* h, const float* q, int64_t nq, int k,
                           float* D, int64_t* I, int ptrs_are_device, int64_t id_offset,
                           int path, kirag_search_stats_t* stats, void* stream);
+
+/* Stream-ordered half of a device-pointer search (KIRAG_PATH_AUTO, nq <= 16384): enqueues every kernel of the
+ * first attempt (filter levels, fp32 rescoring, final sort, certificate) and the copy of the certificate flags to
+ * pinned host memory on `stream` and returns WITHOUT synchronising.  D/I then hold the answer of every query whose
+ * certificate passed (all of them on well-spread data); the caller may enqueue further work that consumes them.
+ * No cudaMalloc / pageable copy happens once the workspaces are warm (one earlier call with the same nq and k), so
+ * the call can be captured into a CUDA graph.  The search is completed by kirag_index_search_finish; any other
+ * call on the handle completes it implicitly first.  q/D/I must stay valid until then. */
+int kirag_index_search_async(kirag_index_t* h, const float* q, int64_t nq, int k,
+                             float* D, int64_t* I, int64_t id_offset, void* stream);
+
+/* Second half: waits for the asynchronous search (the event recorded on its stream; after a graph replay the
+ * stream it was captured on is synchronised instead), examines the certificate flags and re-answers flagged
+ * queries in place (second bf16 pass with the provable threshold, exact fp32 scan as the last resort).
+ * n_changed (optional) = number of queries whose rows of D/I were rewritten: consumers that already read D/I
+ * (e.g. an exchange between GPUs) must run again when it is non-zero.  Returns with the stream idle. */
+int kirag_index_search_finish(kirag_index_t* h, kirag_search_stats_t* stats, int64_t* n_changed);
+
+/* Device pointer to the per-query certificate flags of the pending asynchronous search (int32 [nq]: 0 certified,
+ * 1 certificate failed, 2 candidate buffer overflowed), NULL if nothing is pending or the exact path answered.
+ * Lets a following kernel (the multi-GPU exchange) carry the flags along without a host round trip. */
+int kirag_index_search_flags(const kirag_index_t* h, const int** flags_dev);
 
 /* index.reconstruct_n(i0, n): copy rows [i0, i0+n) of the fp32 master out. */
 int kirag_index_reconstruct(const kirag_index_t* h, int64_t i0, int64_t n, float* out,
@@ -200,15 +228,32 @@ int kirag_exchange_connect_ptrs(kirag_exchange_t* x, void* const* peer_buffers);
 void* kirag_exchange_buffer(kirag_exchange_t* x);
 /* D_loc/I_loc: this rank's per-shard result [nq,k] (device, rows sorted by (score desc, id asc), global
  * ids, padding id -1); D_out/I_out: the global top-k [nq,k] (device), identical on every rank.
- * Stream-ordered; the kernel spins (bounded, ~20 s) until every peer's call has delivered. */
+ * Stream-ordered; the kernel spins (bounded, ~20 s) until every peer's call has delivered.  Every exchange of a
+ * rank must be enqueued on the SAME stream (the first call fixes it; another stream is rejected): the buffers are
+ * double-buffered by call parity, which is only safe if a rank's exchanges execute in call order. */
 int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, int64_t nq, int k,
                               float* D_out, int64_t* I_out, void* stream);
 
+/* Same, and every rank's per-query certificate flags (int32 [nq], device: kirag_index_search_flags of the pending
+ * asynchronous search) travel with its rows; the kernel ORs them over all ranks and queries.  The result — read
+ * with kirag_exchange_last_any_flag once the stream has been synchronised — is IDENTICAL on every rank, so all
+ * ranks decide together, without a host collective, whether some rank has to re-answer queries
+ * (kirag_index_search_finish) and the exchange has to run again.  nq <= the max_nq given at creation. */
+int kirag_exchange_merge_topk_flags(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, const int* flags_loc,
+                                    int64_t nq, int k, float* D_out, int64_t* I_out, void* stream);
+/* OR of the flags carried by the last kirag_exchange_merge_topk_flags call (valid after its stream was synchronised);
+ * -2 (kirag_last_error() set) if an exchange timed out waiting for a peer. */
+int kirag_exchange_last_any_flag(kirag_exchange_t* x);
+
 /* torch.topk(torch.matmul(Q, T.T), k, dim=1)   knowledge_graph/models.py:1532-1538
  * One-shot search over a transient candidate matrix T [nt, d] (device or host
- * pointers, no persistent index). */
+ * pointers).  T is indexed in a per-(device, d) scratch index owned by the library whose device
+ * buffers are kept between calls (no allocation once warm); calls are serialised by a mutex.
+ * Synchronises like kirag_index_search. */
 int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d, int k,
                   float* D, int64_t* I, int ptrs_are_device, int device, void* stream);
+/* Frees the scratch indexes of kirag_topk_ip (optional; e.g. before a process gives a GPU back). */
+int kirag_topk_ip_release(void);
 
 /* ---- embedding epilogue (replaces average_pool + F.normalize) ---------- */
 

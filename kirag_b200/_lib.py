@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkirag_b200.so")
 
 # constants mirrored from the header
-ABI_VERSION = 3
+ABI_VERSION = 4
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 PATH_AUTO, PATH_EXACT, PATH_FAST = 0, 1, 2
@@ -64,6 +64,9 @@ SIGNATURES = {
     "kirag_index_search": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "kirag_index_search_ex": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int64, c_int,
                                       POINTER(SearchStats), c_void_p]),
+    "kirag_index_search_async": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "kirag_index_search_finish": (c_int, [c_void_p, POINTER(SearchStats), POINTER(c_int64)]),
+    "kirag_index_search_flags": (c_int, [c_void_p, POINTER(c_void_p)]),
     "kirag_index_reconstruct": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "kirag_index_save": (c_int, [c_void_p, c_char_p]),
     "kirag_index_load": (c_int, [c_char_p, c_int, POINTER(c_void_p)]),
@@ -80,8 +83,12 @@ SIGNATURES = {
     "kirag_exchange_connect_ptrs": (c_int, [c_void_p, POINTER(c_void_p)]),
     "kirag_exchange_buffer": (c_void_p, [c_void_p]),
     "kirag_exchange_merge_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "kirag_exchange_merge_topk_flags": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                                c_void_p]),
+    "kirag_exchange_last_any_flag": (c_int, [c_void_p]),
     "kirag_topk_ip": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                               c_void_p]),
+    "kirag_topk_ip_release": (c_int, []),
     "kirag_pool_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                      c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "kirag_pool_normalize_fwd_saved": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,

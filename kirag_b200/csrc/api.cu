@@ -169,6 +169,32 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
 
 using namespace kirag;
 
+struct FastParams {
+    int kprime;
+    int growth_override;  // KIRAG_LEVEL_GROWTH (0: automatic)
+    int cap_override;     // KIRAG_CAND_CAP (0: automatic)
+};
+
+struct SearchCounters {
+    int64_t n_fast = 0, n_exact = 0, n_cert_fail = 0, n_overflow = 0, n_rescan = 0, n_changed = 0;
+    int levels = 0;
+};
+
+// An asynchronous search (kirag_index_search_async) whose certificate flags have not been examined yet.
+struct PendingSearch {
+    bool active = false;
+    bool ev_recorded = false;  // false when the call was captured into a CUDA graph (events cannot be waited on then)
+    bool fast_ok = false;
+    int mode = 0, path = 0, k = 0;
+    int64_t nq = 0, id_offset = 0;
+    const float* qd = nullptr;
+    float* Dd = nullptr;
+    int64_t* Id = nullptr;
+    cudaStream_t st = nullptr;
+    long long launches0 = 0;
+    SearchCounters counters;
+};
+
 struct kirag_index {
     int d = 0;
     int metric = 0;
@@ -186,6 +212,8 @@ struct kirag_index {
     DevBuf dense, stage_a, stage_b, qmap, qsel, qnorm2;
     int* host_flags = nullptr;  // pinned: certificate read-back without a staging copy
     size_t host_flags_n = 0;
+    PendingSearch pending;
+    cudaEvent_t pending_ev = nullptr;
 };
 
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -301,13 +329,9 @@ static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, 
 // Small query batches (<= kWideCapMaxQueries) get a 4x larger candidate buffer: the filter has slack
 // there (HBM-bound), launches are what costs, and a 4x larger g_max removes two to three levels.
 constexpr int64_t kWideCapMaxQueries = 128;
+constexpr int64_t kQChunk = 16384;  // queries per pass of the search workspaces
 constexpr int kMaxGrowth = 32;
 
-struct FastParams {
-    int kprime;
-    int growth_override;  // KIRAG_LEVEL_GROWTH (0: automatic)
-    int cap_override;     // KIRAG_CAND_CAP (0: automatic)
-};
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -318,9 +342,10 @@ static int env_int(const char* name, int dflt) {
 static bool fast_eligible(const kirag_index* h, int k, FastParams* fp) {
     if (!h->shadow || !scan_tc_supported(h->d)) return false;
     if (h->ntotal > 0x7fffff00LL) return false;
-    int64_t kp = (int64_t)4 * k;  // over-fetch k' = 4k (north_star)
+    int64_t kp = (int64_t)4 * k;  // over-fetch k' = 4k (north_star), at most 2048 (k <= 2048 is checked by the caller)
     if (kp < 32) kp = 32;
-    if (kp > 2048) return false;
+    if (kp > 2048) kp = 2048;
+    if (kp < k) return false;
     fp->kprime = (int)kp;
     fp->growth_override = env_int("KIRAG_LEVEL_GROWTH", 0);
     fp->cap_override = env_int("KIRAG_CAND_CAP", 0);
@@ -530,6 +555,133 @@ static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_a
     return 0;
 }
 
+// ------------------------------------------------ enqueue / resolve of one chunk ----
+// A search is split in two halves so that the certificate never forces a host synchronisation in the
+// middle of the device work:
+//   enqueue_chunk  every kernel of the first attempt (filter levels, rescoring, final sort + certificate) and
+//                  the copy of the per-query certificate flags into pinned host memory.  No synchronisation,
+//                  no pageable copies: stream-ordered and CUDA-graph capturable (workspaces must be warm).
+//   resolve_chunk  AFTER the stream has been synchronised by whoever needs the results: looks at the flags and
+//                  re-answers the flagged queries (second bf16 pass with the provable threshold, then the exact
+//                  fp32 scan for whatever is left).  Flagged queries are rare (none on i.i.d. data).
+
+static int ensure_host_flags(kirag_index* h, int64_t cq) {
+    if (h->host_flags_n >= (size_t)cq) return 0;
+    if (h->host_flags) cudaFreeHost(h->host_flags);
+    h->host_flags = nullptr;
+    h->host_flags_n = 0;
+    const size_t want = (size_t)round_up(cq, 4096);
+    KIRAG_CUDA_OK(cudaHostAlloc((void**)&h->host_flags, want * sizeof(int), cudaHostAllocDefault));
+    h->host_flags_n = want;
+    return 0;
+}
+
+// mode: 0 = nothing to verify (empty index / exact path), 1 = filter path, flags are on their way to host_flags
+static int enqueue_chunk(kirag_index* h, const float* qd, int64_t cq, int k, float* Dd, int64_t* Id, int64_t id_offset,
+                         bool fast_ok, const FastParams& fp, SearchCounters* c, int* mode, cudaStream_t st) {
+    *mode = 0;
+    if (h->ntotal == 0) return launch_fill_pad(Dd, Id, cq * k, st);
+    if (!fast_ok) {
+        if (exact_search(h, qd, cq, k, Dd, Id, 0, nullptr, id_offset, st)) return 1;
+        c->n_exact += cq;
+        return 0;
+    }
+    if (ensure_host_flags(h, cq)) return 1;  // may synchronise the device: before anything is enqueued
+    if (fast_search(h, qd, cq, k, Dd, Id, id_offset, fp, 1, &c->levels, st)) return 1;
+    // one read-back: flags[i] = 0 ok, 1 certificate failed, 2 candidate buffer overflowed
+    KIRAG_CUDA_OK(cudaMemcpyAsync(h->host_flags, h->flags.p, (size_t)cq * 4, cudaMemcpyDeviceToHost, st));
+    *mode = 1;
+    return 0;
+}
+
+// The stream must have been synchronised since enqueue_chunk.  Returns with the stream idle.
+static int resolve_chunk(kirag_index* h, const float* qd, int64_t cq, int k, float* Dd, int64_t* Id, int64_t id_offset,
+                         int path, SearchCounters* c, cudaStream_t st) {
+    const int d = h->d;
+    const int* flags = h->host_flags;
+    std::vector<char> ovf((size_t)cq);
+    std::vector<int> bad;
+    for (int64_t i = 0; i < cq; ++i) {
+        ovf[(size_t)i] = flags[(size_t)i] == 2 ? 1 : 0;
+        if (ovf[(size_t)i]) ++c->n_overflow;
+        if (flags[(size_t)i]) { bad.push_back((int)i); if (!ovf[(size_t)i]) ++c->n_cert_fail; }
+    }
+    if (bad.empty() || path != KIRAG_PATH_AUTO) {
+        c->n_fast += cq;
+        return 0;
+    }
+    // 1st escalation: certificate failures (not overflows) get one more bf16 pass with the provable
+    // threshold; 2nd: whatever is left goes to the exact fp32 scan
+    std::vector<int> rescan, exact;
+    const bool no_rescan = env_int("KIRAG_NO_RESCAN", 0) != 0;
+    for (int b : bad) ((ovf[(size_t)b] || no_rescan) ? exact : rescan).push_back(b);
+    if (!rescan.empty()) {
+        const int64_t nb = (int64_t)rescan.size();
+        if (h->qmap.ensure((size_t)nb * 4)) return 1;
+        if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
+        if (h->qnorm2.ensure((size_t)cq * 8)) return 1;
+        // qnorm / flags buffers are reused by the rescan: keep a copy of the norms (+ error norms)
+        KIRAG_CUDA_OK(cudaMemcpyAsync(h->qnorm2.p, h->qnorm.p, (size_t)cq * 8, cudaMemcpyDeviceToDevice, st));
+        KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, rescan.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
+        KIRAG_LAUNCH_OK("gather_rows_kernel");
+        std::vector<int> still_bad;
+        if (rescan_search(h, h->qsel.as<float>(), h->qnorm2.as<float>(), h->qnorm2.as<float>() + cq, nb, k, Dd, Id,
+                          h->qmap.as<int>(), id_offset, kSelectSeg, &still_bad, st)) return 1;
+        for (int i : still_bad) exact.push_back(rescan[(size_t)i]);
+        c->n_rescan += nb - (int64_t)still_bad.size();
+    }
+    if (!exact.empty()) {
+        const int64_t nb = (int64_t)exact.size();
+        if (h->qmap.ensure((size_t)nb * 4)) return 1;
+        if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
+        KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, exact.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
+        KIRAG_LAUNCH_OK("gather_rows_kernel");
+        if (exact_search(h, h->qsel.as<float>(), nb, k, Dd, Id, 0, h->qmap.as<int>(), id_offset, st)) return 1;
+        c->n_exact += nb;
+    }
+    // exact[] / rescan[] live on this stack frame until the copies above have been consumed
+    KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+    c->n_fast += cq - (int64_t)bad.size();
+    c->n_changed += (int64_t)bad.size();
+    return 0;
+}
+
+static void fill_stats(kirag_search_stats_t* stats, int64_t nq, const SearchCounters& c, bool fast_ok, int path,
+                       long long launches0) {
+    if (!stats) return;
+    stats->nq = nq;
+    stats->n_fast = c.n_fast;
+    stats->n_exact = c.n_exact;
+    stats->n_cert_fail = c.n_cert_fail;
+    stats->n_overflow = c.n_overflow;
+    stats->n_rescan = c.n_rescan;
+    stats->levels = c.levels;
+    stats->path = fast_ok ? path : KIRAG_PATH_EXACT;
+    stats->kernel_launches = g_launches.load() - launches0;
+}
+
+// Completes an asynchronous search whose certificate has not been looked at yet (kirag_index_search_async).
+static int finish_pending(kirag_index* h, kirag_search_stats_t* stats, int64_t* n_changed) {
+    if (n_changed) *n_changed = 0;
+    PendingSearch& p = h->pending;
+    if (!p.active) {
+        if (stats) memset(stats, 0, sizeof(*stats));
+        return 0;
+    }
+    p.active = false;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    if (p.ev_recorded) KIRAG_CUDA_OK(cudaEventSynchronize(h->pending_ev));
+    else KIRAG_CUDA_OK(cudaStreamSynchronize(p.st));
+    SearchCounters c = p.counters;
+    if (p.mode == 1 && resolve_chunk(h, p.qd, p.nq, p.k, p.Dd, p.Id, p.id_offset, p.path, &c, p.st)) return 1;
+    fill_stats(stats, p.nq, c, p.fast_ok, p.path, p.launches0);
+    if (n_changed) *n_changed = c.n_changed;
+    return 0;
+}
+
 static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float* D, int64_t* I,
                        int ptrs_are_device, int64_t id_offset, int path, kirag_search_stats_t* stats,
                        cudaStream_t st) {
@@ -538,6 +690,7 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
     KIRAG_CHECK(k <= 2048, "search: k=%d exceeds the supported maximum of 2048", k);
     KIRAG_CHECK(nq >= 0, "search: negative nq");
     KIRAG_CHECK(path >= 0 && path <= 2, "search: unknown path %d", path);
+    if (finish_pending(h, nullptr, nullptr)) return 1;  // an unfinished asynchronous search owns the workspaces
     if (stats) memset(stats, 0, sizeof(*stats));
     if (nq == 0) return 0;
     KIRAG_CHECK(q && D && I, "search: null buffer");
@@ -545,9 +698,7 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
     if (!guard.ok) return 1;
     const long long launches0 = g_launches.load();
     const int d = h->d;
-    const int64_t kQChunk = 16384;
-    int64_t n_fast = 0, n_exact = 0, n_cert_fail = 0, n_overflow = 0, n_rescan = 0;
-    int levels = 0;
+    SearchCounters c;
     FastParams fp{};
     const bool fast_ok = (path != KIRAG_PATH_EXACT) && h->ntotal > 0 && fast_eligible(h, k, &fp);
 
@@ -565,90 +716,25 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
             KIRAG_CUDA_OK(cudaMemcpyAsync(h->q_dev.p, q + q0 * d, (size_t)cq * d * 4, cudaMemcpyHostToDevice, st));
             qd = h->q_dev.as<float>(); Dd = h->D_dev.as<float>(); Id = h->I_dev.as<int64_t>();
         }
-        if (h->ntotal == 0) {
-            if (launch_fill_pad(Dd, Id, cq * k, st)) return 1;
-        } else if (!fast_ok) {
-            if (exact_search(h, qd, cq, k, Dd, Id, 0, nullptr, id_offset, st)) return 1;
-            n_exact += cq;
-        } else {
-            const int check = 1;
-            if (fast_search(h, qd, cq, k, Dd, Id, id_offset, fp, check, &levels, st)) return 1;
-            // certificate outcome
-            // one read-back: flags[i] = 0 ok, 1 certificate failed, 2 candidate buffer overflowed
-            if (h->host_flags_n < (size_t)cq) {
-                if (h->host_flags) cudaFreeHost(h->host_flags);
-                h->host_flags = nullptr;
-                h->host_flags_n = 0;
-                const size_t want = (size_t)round_up(cq, 4096);
-                KIRAG_CUDA_OK(cudaHostAlloc((void**)&h->host_flags, want * sizeof(int), cudaHostAllocDefault));
-                h->host_flags_n = want;
-            }
-            const int* flags = h->host_flags;
-            std::vector<char> ovf((size_t)cq);
-            KIRAG_CUDA_OK(cudaMemcpyAsync(h->host_flags, h->flags.p, (size_t)cq * 4, cudaMemcpyDeviceToHost, st));
-            KIRAG_CUDA_OK(cudaStreamSynchronize(st));
-            std::vector<int> bad;
-            for (int64_t i = 0; i < cq; ++i) {
-                ovf[(size_t)i] = flags[(size_t)i] == 2 ? 1 : 0;
-                if (ovf[i]) ++n_overflow;
-                if (flags[i]) { bad.push_back((int)i); if (!ovf[i]) ++n_cert_fail; }
-            }
-            if (!bad.empty() && path == KIRAG_PATH_AUTO) {
-                // 1st escalation: certificate failures (not overflows) get one more bf16 pass with the
-                // provable threshold; 2nd: whatever is left goes to the exact fp32 scan
-                std::vector<int> rescan, exact;
-                for (int b : bad) (ovf[(size_t)b] || env_int("KIRAG_NO_RESCAN", 0) ? exact : rescan).push_back(b);
-                if (!rescan.empty()) {
-                    const int64_t nb = (int64_t)rescan.size();
-                    if (h->qmap.ensure((size_t)nb * 4)) return 1;
-                    if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
-                    if (h->qnorm2.ensure((size_t)cq * 8)) return 1;
-                    // qnorm / flags buffers are reused by the rescan: keep a copy of the norms (+ error norms)
-                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qnorm2.p, h->qnorm.p, (size_t)cq * 8, cudaMemcpyDeviceToDevice, st));
-                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, rescan.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-                    gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
-                    KIRAG_LAUNCH_OK("gather_rows_kernel");
-                    std::vector<int> still_bad;
-                    if (rescan_search(h, h->qsel.as<float>(), h->qnorm2.as<float>(), h->qnorm2.as<float>() + cq, nb, k, Dd, Id,
-                                      h->qmap.as<int>(),
-                                      id_offset, kSelectSeg, &still_bad, st)) return 1;
-                    for (int i : still_bad) exact.push_back(rescan[(size_t)i]);
-                    n_rescan += nb - (int64_t)still_bad.size();
-                }
-                if (!exact.empty()) {
-                    const int64_t nb = (int64_t)exact.size();
-                    if (h->qmap.ensure((size_t)nb * 4)) return 1;
-                    if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
-                    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, exact.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-                    gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
-                    KIRAG_LAUNCH_OK("gather_rows_kernel");
-                    if (exact_search(h, h->qsel.as<float>(), nb, k, Dd, Id, 0, h->qmap.as<int>(), id_offset, st)) return 1;
-                    // exact[] lives on the host stack frame until the copy above has been consumed
-                    KIRAG_CUDA_OK(cudaStreamSynchronize(st));
-                    n_exact += nb;
-                }
-                n_fast += cq - (int64_t)bad.size();
-            } else {
-                n_fast += cq;
-            }
-        }
+        int mode = 0;
+        if (enqueue_chunk(h, qd, cq, k, Dd, Id, id_offset, fast_ok, fp, &c, &mode, st)) return 1;
+        // host buffers: the results travel with the certificate flags, ONE synchronisation per chunk
         if (!ptrs_are_device) {
             KIRAG_CUDA_OK(cudaMemcpyAsync(D + q0 * k, Dd, (size_t)cq * k * 4, cudaMemcpyDeviceToHost, st));
             KIRAG_CUDA_OK(cudaMemcpyAsync(I + q0 * k, Id, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, st));
-            KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        if (mode == 1 || !ptrs_are_device) KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+        if (mode == 1) {
+            const int64_t changed0 = c.n_changed;
+            if (resolve_chunk(h, qd, cq, k, Dd, Id, id_offset, path, &c, st)) return 1;
+            if (!ptrs_are_device && c.n_changed != changed0) {  // some rows were re-answered: fetch them again
+                KIRAG_CUDA_OK(cudaMemcpyAsync(D + q0 * k, Dd, (size_t)cq * k * 4, cudaMemcpyDeviceToHost, st));
+                KIRAG_CUDA_OK(cudaMemcpyAsync(I + q0 * k, Id, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, st));
+                KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+            }
         }
     }
-    if (stats) {
-        stats->nq = nq;
-        stats->n_fast = n_fast;
-        stats->n_exact = n_exact;
-        stats->n_cert_fail = n_cert_fail;
-        stats->n_overflow = n_overflow;
-        stats->n_rescan = n_rescan;
-        stats->levels = levels;
-        stats->path = fast_ok ? path : KIRAG_PATH_EXACT;
-        stats->kernel_launches = g_launches.load() - launches0;
-    }
+    fill_stats(stats, nq, c, fast_ok, path, launches0);
     return 0;
 }
 
@@ -773,6 +859,7 @@ int kirag_index_destroy(kirag_index_t* h) {
                       &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel, &h->qnorm2};
     for (DevBuf* b : bufs) b->release();
     if (h->host_flags) cudaFreeHost(h->host_flags);
+    if (h->pending_ev) cudaEventDestroy(h->pending_ev);
     delete h;
     return 0;
 }
@@ -793,6 +880,7 @@ int kirag_index_add(kirag_index_t* h, const float* x, int64_t n, int x_is_device
     DeviceGuard guard(h->device);
     if (!guard.ok) return 1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (finish_pending(h, nullptr, nullptr)) return 1;
     KIRAG_CHECK(h->ntotal + n <= 0x7fffff00LL, "index_add: more than 2^31 rows per device are not supported");
     if (index_grow(h, h->ntotal + n, st)) return 1;
     float* dst = h->master + h->ntotal * (int64_t)h->d;
@@ -823,6 +911,49 @@ int kirag_index_search_ex(kirag_index_t* h, const float* q, int64_t nq, int k, f
                           int ptrs_are_device, int64_t id_offset, int path, kirag_search_stats_t* stats,
                           void* stream) {
     return search_impl(h, q, nq, k, D, I, ptrs_are_device, id_offset, path, stats, (cudaStream_t)stream);
+}
+
+int kirag_index_search_async(kirag_index_t* h, const float* q, int64_t nq, int k, float* D, int64_t* I,
+                             int64_t id_offset, void* stream) {
+    KIRAG_CHECK(h != nullptr, "search_async: null index");
+    KIRAG_CHECK(k > 0 && k <= 2048, "search_async: k=%d not in [1, 2048]", k);
+    KIRAG_CHECK(nq >= 0 && nq <= kQChunk, "search_async: nq=%lld not in [0, %lld] (split larger batches)", (long long)nq,
+                (long long)kQChunk);
+    if (finish_pending(h, nullptr, nullptr)) return 1;
+    if (nq == 0) return 0;
+    KIRAG_CHECK(q && D && I, "search_async: null buffer");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    PendingSearch& p = h->pending;
+    p = PendingSearch();
+    p.launches0 = g_launches.load();
+    FastParams fp{};
+    p.fast_ok = h->ntotal > 0 && fast_eligible(h, k, &fp);
+    p.path = KIRAG_PATH_AUTO;
+    if (enqueue_chunk(h, q, nq, k, D, I, id_offset, p.fast_ok, fp, &p.counters, &p.mode, st)) return 1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+        if (!h->pending_ev) KIRAG_CUDA_OK(cudaEventCreateWithFlags(&h->pending_ev, cudaEventDisableTiming));
+        KIRAG_CUDA_OK(cudaEventRecord(h->pending_ev, st));
+        p.ev_recorded = true;
+    }
+    p.nq = nq; p.k = k; p.id_offset = id_offset;
+    p.qd = q; p.Dd = D; p.Id = I; p.st = st;
+    p.active = true;
+    return 0;
+}
+
+int kirag_index_search_finish(kirag_index_t* h, kirag_search_stats_t* stats, int64_t* n_changed) {
+    KIRAG_CHECK(h != nullptr, "search_finish: null index");
+    return finish_pending(h, stats, n_changed);
+}
+
+int kirag_index_search_flags(const kirag_index_t* h, const int** flags_dev) {
+    KIRAG_CHECK(h != nullptr && flags_dev != nullptr, "search_flags: null argument");
+    *flags_dev = (h->pending.active && h->pending.mode == 1) ? h->flags.as<int>() : nullptr;
+    return 0;
 }
 
 int kirag_index_reconstruct(const kirag_index_t* h, int64_t i0, int64_t n, float* out, int out_is_device,
@@ -898,7 +1029,8 @@ int kirag_debug_level_schedule(int64_t n_rows, int64_t nq, int k, int d, int64_t
     }
     int64_t kp = (int64_t)4 * k;
     if (kp < 32) kp = 32;
-    if (kp > 2048 || !scan_tc_supported(d) || n_rows > 0x7fffff00LL) return -1;  // not eligible for the filter path
+    if (kp > 2048) kp = 2048;
+    if (kp < k || !scan_tc_supported(d) || n_rows > 0x7fffff00LL) return -1;  // not eligible for the filter path
     FastParams fp{};
     fp.kprime = (int)kp;
     fp.growth_override = env_int("KIRAG_LEVEL_GROWTH", 0);
@@ -1048,23 +1180,44 @@ int kirag_merge_topk(const float* D_all, const int64_t* I_all, int G, int64_t nq
     return rc;
 }
 
+// The transient candidate matrix of a call is indexed in a per-(device, d) scratch index that is kept
+// between calls: its device buffers (fp32 copy, bf16 shadow, search workspaces) are allocated once and
+// grow-only, so a call costs one copy + one convert pass over T and one search — no cudaMalloc / cudaFree /
+// device-wide synchronisation per call.
+struct ScratchIndex { int device; int d; kirag_index_t* h; };
+static std::vector<ScratchIndex> g_scratch;
+static std::mutex g_scratch_mu;
+
 int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d, int k, float* D, int64_t* I,
                   int ptrs_are_device, int device, void* stream) {
     KIRAG_CHECK(nt >= 0 && nq >= 0, "topk_ip: negative size");
+    std::lock_guard<std::mutex> lock(g_scratch_mu);  // calls on one (device, d) share the scratch index
     kirag_index_t* h = nullptr;
-    if (kirag_index_create(d, KIRAG_METRIC_INNER_PRODUCT, device, &h)) return 1;
+    for (auto& e : g_scratch)
+        if (e.device == device && e.d == d) h = e.h;
+    if (!h) {
+        if (kirag_index_create(d, KIRAG_METRIC_INNER_PRODUCT, device, &h)) return 1;
+        g_scratch.push_back({device, d, h});
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (finish_pending(h, nullptr, nullptr)) return 1;
+    // forget the previous call's rows (capacity and workspaces stay)
+    h->ntotal = 0;
+    h->maxnorm = h->maxerr = 0.f;
+    KIRAG_CUDA_OK(cudaMemsetAsync(h->maxnorm2_bits, 0, 8, st));
     int rc = 0;
     if (nt > 0) rc = kirag_index_add(h, t, nt, ptrs_are_device, stream);
     if (!rc) rc = kirag_index_search(h, q, nq, k, D, I, ptrs_are_device, 0, stream);
-    if (!rc && ptrs_are_device) {
-        DeviceGuard guard(device);
-        if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
-            set_error("topk_ip: stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = 1;
-        }
-    }
-    kirag_index_destroy(h);
     return rc;
+}
+
+int kirag_topk_ip_release(void) {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    for (auto& e : g_scratch) kirag_index_destroy(e.h);
+    g_scratch.clear();
+    return 0;
 }
 
 int kirag_pool_normalize(const void* hidden, const void* mask, float* out, int64_t B, int64_t S, int64_t H,

@@ -19,8 +19,9 @@
 // (it cannot finish call e before every peer has STARTED call e, i.e. finished call e-1), so
 // data of call e+1 never lands in a slot that call e-1 is still reading.
 // Every CTA pushes before it waits and the grid is small enough to be co-resident, so the wait
-// cannot deadlock; it is bounded anyway (trap after ~20 s) so that a dead peer is an error, not
-// a hang.
+// cannot deadlock; it is bounded anyway (~20 s) so that a dead peer is an error, not a hang: the kernel
+// then writes the offending rank into a mapped host word and returns (no trap: the context stays usable),
+// and the next call on the exchange object fails with that message.
 #include "common.cuh"
 #include "../../include/kirag_b200.h"
 
@@ -43,6 +44,8 @@ struct ExchangeArgs {
     size_t slot_bytes;   // capacity of one (parity, source rank) slot
     size_t flags_off;    // byte offset of the flag region
     size_t ids_off;      // byte offset of the id block inside a slot for this call (after nq*k scores)
+                         // NB: the field `flags_off` above is the barrier-flag region of the whole buffer; the
+                         // per-query certificate flags live at `qflags_off` inside every slot
     const float* D_loc;
     const int64_t* I_loc;
     float* D_out;
@@ -50,6 +53,10 @@ struct ExchangeArgs {
     int vec16;     // rows can be copied with 16-byte accesses (k % 4 == 0, aligned bases)
     int n_groups;  // thread groups per CTA in the merge phase (1, 2 or 4), one query each at a time
     int tree;      // 1: pairwise merge tree (needs two list buffers in shared memory), 0: rank-everything merge
+    const int* flags_loc;  // optional: this rank's per-query certificate flags (device), carried along with the rows
+    size_t qflags_off;     // byte offset of the per-query flag block inside a slot (fixed per exchange object)
+    int* any_flag;         // device: OR over all ranks and queries of the carried flags (identical on every rank)
+    int* timeout_word;     // mapped pinned host word: set to 1 + source rank if a peer never delivered
 };
 
 __device__ __forceinline__ uint8_t* slot_ptr(const ExchangeArgs& a, int dst, int src) {
@@ -120,6 +127,10 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
                 si[i] = a.I_loc[i];
             }
         }
+        if (a.flags_loc) {
+            int* sf = reinterpret_cast<int*>(slot + a.qflags_off);
+            for (int64_t qq = q_lo + threadIdx.x; qq < q_hi; qq += blockDim.x) sf[qq] = a.flags_loc[qq];
+        }
     }
     __syncthreads();
     if (threadIdx.x < G) {
@@ -128,6 +139,9 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
         st_release_sys(flag_ptr(a, threadIdx.x, a.rank, b), a.epoch);
     }
     // ------------------------------------------------------------------ wait ----
+    __shared__ int s_timed_out;
+    if (threadIdx.x == 0) s_timed_out = 0;
+    __syncthreads();
     if (threadIdx.x < G) {
         const int* f = flag_ptr(a, a.rank, threadIdx.x, b);
         if (ld_acquire_sys(f) != a.epoch) {
@@ -135,15 +149,30 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
             while (ld_acquire_sys(f) != a.epoch) {
                 __nanosleep(64);
                 if (clock64() - t0 > 40000000000LL) {
+                    // a peer never delivered (~20 s): report through the mapped host word and leave the kernel;
+                    // the context stays usable and the host turns the word into an error status
                     printf("kirag exchange: rank %d block %d timed out waiting for rank %d (epoch %d, flag %d)\n",
                            a.rank, b, (int)threadIdx.x, a.epoch, ld_acquire_sys(f));
-                    __trap();
+                    *reinterpret_cast<volatile int*>(a.timeout_word) = 1 + (int)threadIdx.x;
+                    __threadfence_system();
+                    s_timed_out = 1;
+                    break;
                 }
             }
         }
         __threadfence_system();
     }
     __syncthreads();
+    if (s_timed_out) return;
+    if (a.flags_loc) {
+        // OR of every rank's certificate flags for this CTA's queries: the same value on every rank, so all
+        // ranks take the same decision about re-answering without a host collective
+        int mine = 0;
+        for (int64_t qq = q_lo + threadIdx.x; qq < q_hi; qq += blockDim.x)
+            for (int g = 0; g < G; ++g)
+                mine |= __ldcg(reinterpret_cast<const int*>(slot_ptr(a, a.rank, g) + a.qflags_off) + qq);
+        if (__any_sync(0xffffffffu, mine != 0) && (threadIdx.x & 31) == 0) atomicOr(a.any_flag, 1);
+    }
     // ----------------------------------------------------------------- merge ----
     // The CTA splits into n_groups thread groups; each merges one query at a time in its own slice of
     // shared memory and synchronises with a named barrier of its own.
@@ -271,6 +300,12 @@ struct kirag_exchange {
     bool opened[kMaxRanks] = {false};  // mapped with cudaIpcOpenMemHandle (to be closed)
     bool connected = false;
     int epoch = 0;
+    size_t qflags_off = 0;       // per-query certificate flags inside a slot
+    int64_t qflags_cap = 0;      // queries the flag block of a slot can hold
+    int* any_dev = nullptr;      // [2] by parity
+    int* any_host = nullptr;     // pinned + mapped, [0..1] by parity: OR of the carried flags; [2]: time-out word
+    cudaStream_t stream = nullptr;  // the stream of the first exchange: every later call must use it (epoch
+    bool stream_set = false;        // double-buffering is only safe if a rank's calls execute in order)
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -306,7 +341,9 @@ int kirag_exchange_create(int device, int rank, int world, int64_t max_nq, int m
     x->world = world;
     x->max_nq = max_nq;
     x->max_k = max_k;
-    x->slot_bytes = align_up((size_t)max_nq * max_k * 4, 16) + align_up((size_t)max_nq * max_k * 8, 16);
+    x->qflags_off = align_up((size_t)max_nq * max_k * 4, 16) + align_up((size_t)max_nq * max_k * 8, 16);
+    x->qflags_cap = max_nq;
+    x->slot_bytes = x->qflags_off + align_up((size_t)x->qflags_cap * 4, 16);
     x->flags_off = align_up(2 * (size_t)world * x->slot_bytes, 256);
     x->total_bytes = x->flags_off + 2 * (size_t)kMaxRanks * kExchangeMaxBlocks * sizeof(int);
     cudaError_t e = cudaMalloc((void**)&x->own, x->total_bytes);
@@ -325,6 +362,17 @@ int kirag_exchange_create(int device, int rank, int world, int64_t max_nq, int m
         if (prev >= 0) cudaSetDevice(prev);
         return 1;
     }
+    if (cudaMalloc((void**)&x->any_dev, 2 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(x->any_dev, 0, 2 * sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc((void**)&x->any_host, 4 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        set_error("exchange_create: allocating the flag words failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (x->any_dev) cudaFree(x->any_dev);
+        cudaFree(x->own);
+        delete x;
+        if (prev >= 0) cudaSetDevice(prev);
+        return 1;
+    }
+    x->any_host[0] = x->any_host[1] = x->any_host[2] = x->any_host[3] = 0;
     x->peer[rank] = x->own;
     if (world == 1) x->connected = true;
     if (prev >= 0) cudaSetDevice(prev);
@@ -341,6 +389,8 @@ int kirag_exchange_destroy(kirag_exchange_t* x) {
     for (int g = 0; g < x->world; ++g)
         if (x->opened[g] && x->peer[g]) cudaIpcCloseMemHandle(x->peer[g]);
     if (x->own) cudaFree(x->own);
+    if (x->any_dev) cudaFree(x->any_dev);
+    if (x->any_host) cudaFreeHost(x->any_host);
     delete x;
     if (prev >= 0) cudaSetDevice(prev);
     return 0;
@@ -385,6 +435,24 @@ int kirag_exchange_connect_ptrs(kirag_exchange_t* x, void* const* peer_buffers) 
     for (int g = 0; g < x->world; ++g) {
         if (g == x->rank) continue;
         KIRAG_CHECK(peer_buffers[g] != nullptr, "exchange_connect_ptrs: null buffer for rank %d", g);
+        // a buffer on another device must be peer-accessible from this rank's device (same device: always fine)
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, peer_buffers[g]) == cudaSuccess && attr.type == cudaMemoryTypeDevice &&
+            attr.device != x->device) {
+            int can = 0;
+            KIRAG_CUDA_OK(cudaDeviceCanAccessPeer(&can, x->device, attr.device));
+            KIRAG_CHECK(can, "exchange_connect_ptrs: device %d cannot access rank %d's buffer on device %d", x->device, g,
+                        attr.device);
+            DeviceGuardLite guard(x->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                set_error("exchange_connect_ptrs: cudaDeviceEnablePeerAccess(%d) failed: %s", attr.device, cudaGetErrorString(e));
+                return 1;
+            }
+            cudaGetLastError();
+        } else {
+            cudaGetLastError();
+        }
         x->peer[g] = static_cast<uint8_t*>(peer_buffers[g]);
     }
     x->connected = true;
@@ -393,8 +461,8 @@ int kirag_exchange_connect_ptrs(kirag_exchange_t* x, void* const* peer_buffers) 
 
 void* kirag_exchange_buffer(kirag_exchange_t* x) { return x ? x->own : nullptr; }
 
-int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, int64_t nq, int k,
-                              float* D_out, int64_t* I_out, void* stream) {
+static int exchange_merge_impl(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, const int* flags_loc,
+                               int64_t nq, int k, float* D_out, int64_t* I_out, void* stream) {
     KIRAG_CHECK(x != nullptr, "exchange_merge: null exchange");
     KIRAG_CHECK(x->connected, "exchange_merge: peers are not connected (call kirag_exchange_connect first)");
     KIRAG_CHECK(k > 0 && k <= x->max_k, "exchange_merge: k=%d not in [1, %d]", k, x->max_k);
@@ -403,6 +471,16 @@ int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int
                 (long long)(x->max_nq * x->max_k));
     if (nq == 0) return 0;
     KIRAG_CHECK(D_loc && I_loc && D_out && I_out, "exchange_merge: null buffer");
+    KIRAG_CHECK(!flags_loc || nq <= x->qflags_cap, "exchange_merge: nq=%lld exceeds the flag capacity %lld", (long long)nq,
+                (long long)x->qflags_cap);
+    // Epoch double-buffering assumes that this rank's exchanges execute in call order: they must all be enqueued
+    // on one stream (the first call fixes it).
+    KIRAG_CHECK(x->any_host[2] == 0, "exchange_merge: an earlier exchange timed out waiting for rank %d (a peer died or "
+                "skipped a call); this exchange object is no longer usable", x->any_host[2] - 1);
+    if (!x->stream_set) { x->stream = (cudaStream_t)stream; x->stream_set = true; }
+    KIRAG_CHECK(x->stream == (cudaStream_t)stream,
+                "exchange_merge: every exchange of a rank must be enqueued on the same stream (first call used %p, this one %p)",
+                (void*)x->stream, stream);
     DeviceGuardLite guard(x->device);
     ExchangeArgs a{};
     for (int g = 0; g < x->world; ++g) a.peer[g] = x->peer[g];
@@ -435,9 +513,37 @@ int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int
               ((reinterpret_cast<uintptr_t>(I_loc) & 15) == 0) && ((a.ids_off & 15) == 0);
     const size_t smem = per_query * n_groups;
     if (smem > 48 * 1024 && ensure_dynamic_smem(exchange_merge_kernel, 96 * 1024)) return 1;
+    a.flags_loc = flags_loc;
+    a.qflags_off = x->qflags_off;
+    a.any_flag = x->any_dev + a.parity;
+    a.timeout_word = x->any_host + 2;  // mapped pinned memory: same address on the device under UVA
+    if (flags_loc) KIRAG_CUDA_OK(cudaMemsetAsync(a.any_flag, 0, sizeof(int), (cudaStream_t)stream));
     exchange_merge_kernel<<<blocks, kExchangeThreads, smem, (cudaStream_t)stream>>>(a);
     KIRAG_LAUNCH_OK("exchange_merge_kernel");
+    if (flags_loc)
+        KIRAG_CUDA_OK(cudaMemcpyAsync(x->any_host + a.parity, a.any_flag, sizeof(int), cudaMemcpyDeviceToHost,
+                                      (cudaStream_t)stream));
     return 0;
+}
+
+int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, int64_t nq, int k,
+                              float* D_out, int64_t* I_out, void* stream) {
+    return exchange_merge_impl(x, D_loc, I_loc, nullptr, nq, k, D_out, I_out, stream);
+}
+
+int kirag_exchange_merge_topk_flags(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, const int* flags_loc,
+                                    int64_t nq, int k, float* D_out, int64_t* I_out, void* stream) {
+    KIRAG_CHECK(flags_loc != nullptr, "exchange_merge_flags: null flags");
+    return exchange_merge_impl(x, D_loc, I_loc, flags_loc, nq, k, D_out, I_out, stream);
+}
+
+int kirag_exchange_last_any_flag(kirag_exchange_t* x) {
+    if (!x) return -1;
+    if (x->any_host[2] != 0) {
+        set_error("exchange: timed out waiting for rank %d", x->any_host[2] - 1);
+        return -2;
+    }
+    return x->any_host[(unsigned)x->epoch & 1u];
 }
 
 }  // extern "C"

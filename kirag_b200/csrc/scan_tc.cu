@@ -98,6 +98,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// Pull a block into L2 ahead of the shared-memory ring (KIRAG_PF_TILES > 0).  Hypothesis tested in round 2: at the
+// ridge (B ~ 256) the ring (7 x 16 KB of corpus per SM) bounds the HBM bytes in flight (ncu r2a: DRAM 52 %, tensor
+// 57 %), and a prefetch needs no shared-memory slot.  Measured at 21M rows (gpurun_out/r2c_knobs.log): SLOWER at every
+// batch size (B=256 14.6-14.9 vs 12.2-13.4 ms; the extra bulk requests load the same TMA / L2 path), so it is off.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* holder_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)),
                  "r"(ncols)
@@ -220,6 +227,7 @@ struct ScanArgs {
     int x_policy;      // L2 policy of corpus blocks that are re-read per query tile: 1 normal, 2 evict_last
     int q_dep;         // 1: the query shadow is written by the kernel right before this one in the chain
                        // (level 0): the producer must pdl_wait() too; 0: only the filter warps wait
+    int pf_tiles;      // L2 prefetch distance of the corpus stream, in corpus tiles of this CTA (0: off)
     float* dump;       // optional [n_rows, dump_ld] dense approx scores (debug / tests)
     int64_t dump_ld;
 };
@@ -484,7 +492,13 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
                 const int64_t tile = ((a.tile_lo + tp) * a.tile_mult) % a.n_tiles;
                 const uint8_t* xsrc = a.shadow + (size_t)tile * ((size_t)a.d * kTileRows * 2);
                 const uint8_t* qsrc = a.qshadow + (size_t)qt * ((size_t)a.d * BQ * 2);
+                const uint8_t* pfsrc = nullptr;  // the tile this CTA streams pf_tiles tiles from now
+                if (a.pf_tiles > 0 && qt == 0 && (tp + a.pf_tiles) * n_qt < w_hi) {
+                    const int64_t ptile = ((a.tile_lo + tp + a.pf_tiles) * a.tile_mult) % a.n_tiles;
+                    pfsrc = a.shadow + (size_t)ptile * ((size_t)a.d * kTileRows * 2);
+                }
                 for (int kc = 0; kc < KC; ++kc) {
+                    if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
                     mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
                     uint8_t* dst = stage_base + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
@@ -672,7 +686,13 @@ scan_tc_pair_kernel(const ScanArgs a) {
                 const uint8_t* xsrc = a.shadow + (size_t)tile * ((size_t)a.d * kTileRows * 2);
                 // query shadow is stored in 128-row tiles: this CTA stages tile 2*qt + rank
                 const uint8_t* qsrc = a.qshadow + (size_t)(2 * qt + rank) * ((size_t)a.d * kPairHalfQ * 2);
+                const uint8_t* pfsrc = nullptr;  // the tile this CTA streams pf_tiles work items from now
+                if (a.pf_tiles > 0 && qt == 0 && (p + a.pf_tiles) * n_qt < w_hi) {
+                    int64_t pti = a.tile_lo + 2 * (p + a.pf_tiles) + rank;
+                    if (pti < a.tile_hi) pfsrc = a.shadow + (size_t)((pti * a.tile_mult) % a.n_tiles) * ((size_t)a.d * kTileRows * 2);
+                }
                 for (int kc = 0; kc < KC; ++kc) {
+                    if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
                     mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
                     uint8_t* dst = stage_base + (size_t)s * kPairStageBytes;
                     mbar_expect_tx(&full_bar[s], (uint32_t)kPairStageBytes);
@@ -803,6 +823,24 @@ static int env_flag(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// Grid of a scan launch: one CTA (pair) per SM (pair) with equal contiguous work ranges.  ncu (r2a, B = 256)
+// shows sm__cycles_active between 0.99M and 1.43M of 1.44M elapsed cycles, which suggested cutting long levels
+// into more CTAs than SMs so that the hardware block scheduler balances them (KIRAG_SCAN_WAVES > 1: up to that
+// many ranges per SM, none shorter than `min_items` work items).  Measured at 21M rows (gpurun_out/r2c_knobs.log):
+// no gain at any batch size (B=256 13.3 vs 13.4 ms, B=512 20.5 vs 19.2 ms), so the default stays 1.
+constexpr int64_t kWaveItems = 48;  // corpus tiles (or tile pairs) per range, times the number of query tiles
+static int64_t scan_grid_limit(int64_t work_items, int64_t slots, int64_t min_items) {
+    int waves = env_flag("KIRAG_SCAN_WAVES", 1);
+    if (waves < 1) waves = 1;
+    int64_t limit = slots;
+    if (waves > 1 && min_items > 0) {
+        int64_t ranges = work_items / min_items;  // ranges of at least min_items items
+        if (ranges > slots * waves) ranges = slots * waves;
+        if (ranges > limit) limit = ranges / slots * slots;  // whole waves only
+    }
+    return limit;
+}
+
 template <int PQ, bool RES>
 static size_t pair_fixed_bytes(int d) {
     return 1024 + (2 * kMaxStages + 5) * 8 + 16 + (RES ? (size_t)(d / 64) * PairCfg<PQ, RES>::kQHalfBytes : 0);
@@ -843,7 +881,8 @@ static int launch_scan_pair(const ScanArgs& args_in, int num_sms, cudaStream_t s
     const size_t smem = pair_fixed_bytes<PQ, RES>(args.d) + (size_t)ns * PairCfg<PQ, RES>::kStageBytes;
     if (ensure_dynamic_smem(scan_tc_pair_kernel<PQ, RES>, kSmemLimit)) return 1;
     int64_t pairs = ((args.tile_hi - args.tile_lo + 1) / 2) * ((args.nq + PQ - 1) / PQ);  // work items
-    if (pairs > num_sms / 2) pairs = num_sms / 2;
+    const int64_t max_pairs = scan_grid_limit(pairs, num_sms / 2, ((args.nq + PQ - 1) / PQ) * kWaveItems);
+    if (pairs > max_pairs) pairs = max_pairs;
     if (pairs <= 0) return 0;
     KIRAG_CUDA_OK(launch_chained(scan_tc_pair_kernel<PQ, RES>, dim3((unsigned)(2 * pairs)), dim3(EpiCfg<PQ>::kThreads), smem, st, args));
     KIRAG_LAUNCH_OK("scan_tc_pair_kernel");
@@ -859,7 +898,8 @@ static int launch_scan_t(const ScanArgs& args_in, int num_sms, cudaStream_t st) 
     if (ensure_dynamic_smem(scan_tc_kernel<BQ, RESIDENT>, kSmemLimit)) return 1;
     const int64_t n_qt = (args.nq + BQ - 1) / BQ;
     int64_t grid = (args.tile_hi - args.tile_lo) * n_qt;  // work items
-    if (grid > num_sms) grid = num_sms;
+    const int64_t max_grid = scan_grid_limit(grid, num_sms, n_qt * kWaveItems);
+    if (grid > max_grid) grid = max_grid;
     if (grid <= 0) return 0;
     KIRAG_CUDA_OK(launch_chained(scan_tc_kernel<BQ, RESIDENT>, dim3((unsigned)grid), dim3(EpiCfg<BQ>::kThreads), smem, st, args));
     KIRAG_LAUNCH_OK("scan_tc_kernel");
@@ -900,6 +940,7 @@ int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshado
     args.dump = nullptr;
     args.dump_ld = 0;
     args.x_policy = env_flag("KIRAG_X_POLICY", 2);  // evict_last measured ~2% faster at batch 4096 (less HBM re-read)
+    args.pf_tiles = env_flag("KIRAG_PF_TILES", 0);
     return launch_scan_args(args, plan, num_sms, st);
 }
 

@@ -43,6 +43,7 @@ class IndexFlatIP:
 
     def __init__(self, d: int, device: Optional[int] = None, _handle: Optional[int] = None):
         self._h = None
+        self._pending = None
         self.last_stats: dict = {}
         self._lib = _lib.load()
         if _handle is not None:
@@ -138,22 +139,37 @@ class IndexFlatIP:
         self._h = h
 
     # -- device-resident entry points (additions, not part of faiss) --------
-    def add_device(self, x) -> None:
-        """x: contiguous float32 CUDA torch tensor [n, d] on this index's device."""
-        assert x.is_cuda and x.dim() == 2 and x.shape[1] == self.d and x.is_contiguous()
-        assert str(x.dtype) == "torch.float32"
+    def _own_tensor(self, t, what: str):
+        """A contiguous float32 tensor ON THIS INDEX'S DEVICE with a 16-byte aligned base (the kernels use
+        float4 loads); a tensor of another GPU is rejected instead of being handed to the kernels as a raw pointer."""
         import torch
 
+        assert t.is_cuda and t.dim() == 2 and t.shape[1] == self.d, f"{what}: expected a CUDA tensor [n, {self.d}]"
+        assert t.device.index == self.device, \
+            f"{what}: tensor is on cuda:{t.device.index}, the index lives on cuda:{self.device}"
+        t = t.contiguous()
+        if t.dtype != torch.float32:
+            t = t.float()
+        if t.data_ptr() % 16:
+            t = t.clone()
+        return t
+
+    def add_device(self, x) -> None:
+        """x: float32 CUDA torch tensor [n, d] on this index's device."""
+        import torch
+
+        assert str(x.dtype) == "torch.float32", "add_device: float32 only (faiss add() semantics)"
+        x = self._own_tensor(x, "add_device")
         st = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(self._lib.kirag_index_add(self._h, ctypes.c_void_p(x.data_ptr()), x.shape[0], 1,
                                              ctypes.c_void_p(st)), "add_device")
 
     def search_device(self, q, k: int, id_offset: int = 0, path: int = _lib.PATH_AUTO):
-        """q: float32 CUDA tensor [n, d]; returns CUDA tensors (D [n,k] f32, I [n,k] i64), stream-ordered."""
+        """q: float32 CUDA tensor [n, d]; returns CUDA tensors (D [n,k] f32, I [n,k] i64).  The work is enqueued
+        on the current stream; the call synchronises once to read the certificate flags (see the header)."""
         import torch
 
-        assert q.is_cuda and q.dim() == 2 and q.shape[1] == self.d
-        q = q.contiguous().float()
+        q = self._own_tensor(q, "search_device")
         k = int(k)
         assert k > 0, "k must be positive"
         n = q.shape[0]
@@ -170,6 +186,45 @@ class IndexFlatIP:
             )
         self.last_stats = stats.as_dict()
         return D, I
+
+    def search_device_async(self, q, k: int, id_offset: int = 0):
+        """Stream-ordered first half of search_device (kirag_index_search_async): no host synchronisation, CUDA-graph
+        capturable once the workspaces are warm.  Returns (D, I); they are final for every query whose certificate
+        passed.  Call finish() (after whatever else was enqueued behind it) to complete the search."""
+        import torch
+
+        q = self._own_tensor(q, "search_device_async")
+        k = int(k)
+        assert k > 0, "k must be positive"
+        n = q.shape[0]
+        D = torch.empty((n, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((n, k), dtype=torch.int64, device=q.device)
+        if n:
+            st = torch.cuda.current_stream(q.device).cuda_stream
+            _lib.check(
+                self._lib.kirag_index_search_async(self._h, ctypes.c_void_p(q.data_ptr()), n, k,
+                                                   ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                                   int(id_offset), ctypes.c_void_p(st)),
+                "search_device_async",
+            )
+        self._pending = (q, D, I)  # the library keeps raw pointers until finish()
+        return D, I
+
+    def pending_flags_ptr(self) -> int:
+        """Device address of the pending search's per-query certificate flags (0 if there is nothing to verify)."""
+        p = ctypes.c_void_p()
+        _lib.check(self._lib.kirag_index_search_flags(self._h, ctypes.byref(p)), "search_flags")
+        return int(p.value or 0)
+
+    def finish(self) -> int:
+        """Second half of search_device_async: verifies the certificates, re-answers flagged queries in place.
+        Returns the number of queries whose rows of (D, I) were rewritten."""
+        stats = _lib.SearchStats()
+        changed = ctypes.c_int64(0)
+        _lib.check(self._lib.kirag_index_search_finish(self._h, ctypes.byref(stats), ctypes.byref(changed)), "finish")
+        self.last_stats = stats.as_dict()
+        self._pending = None
+        return int(changed.value)
 
     def debug_scores(self, x) -> np.ndarray:
         """Dense approximate (bf16 tcgen05) scores [ntotal, nq] — test hook."""

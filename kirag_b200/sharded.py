@@ -77,8 +77,22 @@ class PeerExchange:
         self.device, self.rank, self.world_size = int(device), int(rank), int(world_size)
         self.max_nq, self.max_k = int(max_nq), int(max_k)
         h = ctypes.c_void_p()
-        _lib.check(self._lib.kirag_exchange_create(self.device, self.rank, self.world_size, self.max_nq, self.max_k,
-                                                   ctypes.byref(h)), "exchange_create")
+        status = self._lib.kirag_exchange_create(self.device, self.rank, self.world_size, self.max_nq, self.max_k,
+                                                 ctypes.byref(h))
+        err = _lib.last_error() if status else ""
+        if self.world_size > 1:
+            # agree on the outcome of the allocation before anyone waits for handles: a rank that failed here
+            # would otherwise leave the others blocked in the handle exchange below
+            created = [None] * self.world_size
+            dist.all_gather_object(created, (int(status), err), group=group)
+            bad = [(r, e) for r, (st, e) in enumerate(created) if st]
+            if bad:
+                if not status:
+                    self._lib.kirag_exchange_destroy(h)
+                raise PeerExchangeUnavailable("peer-memory exchange buffers could not be allocated: " +
+                                              "; ".join(f"rank {r}: {e}" for r, e in bad))
+        elif status:
+            raise _lib.KiragError(f"exchange_create: {err}")
         self._h = h
         if self.world_size > 1:
             nb = int(self._lib.kirag_exchange_handle_bytes())
@@ -104,21 +118,39 @@ class PeerExchange:
     def fits(self, nq: int, k: int) -> bool:
         return 0 < k <= self.max_k and nq * k <= self.max_nq * self.max_k
 
-    def merge(self, D_loc: torch.Tensor, I_loc: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """D_loc [nq,k] f32, I_loc [nq,k] i64 (this rank's sorted per-shard result) -> global (D, I)."""
+    def merge(self, D_loc: torch.Tensor, I_loc: torch.Tensor, flags_ptr: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """D_loc [nq,k] f32, I_loc [nq,k] i64 (this rank's sorted per-shard result) -> global (D, I).
+        `flags_ptr`: device address of this rank's per-query certificate flags (IndexFlatIP.pending_flags_ptr());
+        when given on EVERY rank, the flags travel with the rows and any_flag() is valid after a stream sync."""
         nq, k = D_loc.shape
         D_loc = D_loc.contiguous()
         I_loc = I_loc.contiguous()
         D = torch.empty_like(D_loc)
         I = torch.empty_like(I_loc)
         st = torch.cuda.current_stream(D_loc.device).cuda_stream
-        _lib.check(
-            self._lib.kirag_exchange_merge_topk(self._h, ctypes.c_void_p(D_loc.data_ptr()),
-                                                ctypes.c_void_p(I_loc.data_ptr()), nq, k,
-                                                ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
-                                                ctypes.c_void_p(st)),
-            "exchange_merge_topk")
+        if flags_ptr:
+            _lib.check(
+                self._lib.kirag_exchange_merge_topk_flags(self._h, ctypes.c_void_p(D_loc.data_ptr()),
+                                                          ctypes.c_void_p(I_loc.data_ptr()), ctypes.c_void_p(flags_ptr),
+                                                          nq, k, ctypes.c_void_p(D.data_ptr()),
+                                                          ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(st)),
+                "exchange_merge_topk_flags")
+        else:
+            _lib.check(
+                self._lib.kirag_exchange_merge_topk(self._h, ctypes.c_void_p(D_loc.data_ptr()),
+                                                    ctypes.c_void_p(I_loc.data_ptr()), nq, k,
+                                                    ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                                    ctypes.c_void_p(st)),
+                "exchange_merge_topk")
         return D, I
+
+    def any_flag(self) -> int:
+        """OR over all ranks and queries of the flags carried by the last merge(..., flags_ptr) (after a stream
+        synchronisation).  The same value on every rank."""
+        v = int(self._lib.kirag_exchange_last_any_flag(self._h))
+        if v < 0:
+            raise _lib.KiragError(f"exchange: {_lib.last_error()}")
+        return v
 
     def close(self) -> None:
         h, self._h = self._h, None
@@ -199,7 +231,30 @@ class ShardedFlatIP:
         return self.index.search_device(q, k, id_offset=self.lo, path=path)
 
     def search(self, q: torch.Tensor, k: int, path: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """q [nq, d] replicated on every rank -> (D [nq,k], I [nq,k]) global result on every rank."""
+        """q [nq, d] replicated on every rank -> (D [nq,k], I [nq,k]) global result on every rank.
+
+        With the peer exchange the certificate of the local search is verified AFTER the exchange: the local search
+        is enqueued without a host synchronisation, its per-query flags travel with the rows, the exchange kernel
+        ORs them over all ranks (the same word on every rank), and only if some rank had to re-answer a query do
+        all ranks run the exchange a second time.  One stream synchronisation per search, at its very end."""
+        nq = q.shape[0]
+        if (path is None and self.peer is not None and self.world_size > 1 and self.peer.fits(nq, k)
+                and 0 < nq <= min(self.peer.max_nq, 16384) and hasattr(self.index, "search_device_async")):
+            D_loc, I_loc = self.index.search_device_async(q, k, id_offset=self.lo)
+            flags_ptr = self.index.pending_flags_ptr()
+            # ranks can only disagree on flags_ptr if one of them holds an empty shard: those carry zeros
+            if not flags_ptr:
+                self._zero_flags = getattr(self, "_zero_flags", None)
+                if self._zero_flags is None or self._zero_flags.numel() < nq:
+                    self._zero_flags = torch.zeros(max(nq, 1024), dtype=torch.int32, device=q.device)
+                flags_ptr = self._zero_flags.data_ptr()
+            D, I = self.peer.merge(D_loc, I_loc, flags_ptr)
+            torch.cuda.current_stream(q.device).synchronize()
+            redo = self.peer.any_flag()
+            self.index.finish()  # re-answers this rank's flagged queries in place (no-op where none were flagged)
+            if redo:
+                D, I = self.peer.merge(D_loc, I_loc)
+            return D, I
         D_loc, I_loc = self.search_local(q, k, path=path)
         return self.exchange_merge(D_loc, I_loc)
 

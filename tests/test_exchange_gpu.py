@@ -72,6 +72,25 @@ class LocalRanks:
         torch.cuda.synchronize()
         return [d.cpu().numpy() for d in Do], [i.cpu().numpy() for i in Io]
 
+    def merge_with_flags(self, D_all, I_all, flags_all):
+        """flags_all: int32 [G, nq]; returns (ids per rank, any_flag per rank)."""
+        G, nq, k = D_all.shape
+        Dd = [torch.from_numpy(D_all[g]).cuda() for g in range(G)]
+        Id = [torch.from_numpy(I_all[g]).cuda() for g in range(G)]
+        Fd = [torch.from_numpy(flags_all[g]).cuda() for g in range(G)]
+        Do = [torch.empty((nq, k), dtype=torch.float32, device="cuda") for _ in range(G)]
+        Io = [torch.empty((nq, k), dtype=torch.int64, device="cuda") for _ in range(G)]
+        torch.cuda.synchronize()
+        for g in range(G):
+            self._lib_mod.check(
+                self.lib.kirag_exchange_merge_topk_flags(self.h[g], ctypes.c_void_p(Dd[g].data_ptr()),
+                                                         ctypes.c_void_p(Id[g].data_ptr()), ctypes.c_void_p(Fd[g].data_ptr()),
+                                                         nq, k, ctypes.c_void_p(Do[g].data_ptr()),
+                                                         ctypes.c_void_p(Io[g].data_ptr()),
+                                                         ctypes.c_void_p(self.streams[g].cuda_stream)), "merge_flags")
+        torch.cuda.synchronize()
+        return [i.cpu().numpy() for i in Io], [int(self.lib.kirag_exchange_last_any_flag(h)) for h in self.h]
+
     def close(self):
         for h in self.h:
             self.lib.kirag_exchange_destroy(h)
@@ -111,6 +130,54 @@ def test_exchange_short_union_pads_like_faiss():
     Do, Io = oracle.merge_topk(D_all, I_all)
     assert np.array_equal(Im[0], Io) and np.array_equal(Dm[0], Do)
     assert np.all(Im[0][:, 9:] == -1) and np.all(Dm[0][:, 9:] == PAD_D)
+
+
+def test_exchange_carries_certificate_flags_to_every_rank():
+    """kirag_exchange_merge_topk_flags: one rank's flagged query makes the OR word non-zero on EVERY rank (all ranks
+    then re-run the exchange together); all-zero flags leave it zero; the merged rows are unaffected."""
+    rng = np.random.default_rng(11)
+    G, nq, k = 4, 37, 20
+    ranks = LocalRanks(G, max_nq=64, max_k=128)
+    try:
+        for call, (fr, fq) in enumerate(((None, None), (2, 36), (None, None), (0, 0), (3, 5))):
+            D_all, I_all = shard_lists(rng, G, nq, k)
+            flags = np.zeros((G, nq), dtype=np.int32)
+            if fr is not None:
+                flags[fr, fq] = 1 + call % 2
+            Io = oracle.merge_topk(D_all, I_all)[1]
+            Im, anyf = ranks.merge_with_flags(D_all, I_all, flags)
+            assert all(np.array_equal(Im[g], Io) for g in range(G)), f"call {call}"
+            assert anyf == [0 if fr is None else 1] * G, f"call {call}: {anyf}"
+            # a flag-less exchange in between keeps working on the same buffers (parity alternates)
+            Dm2, Im2 = ranks.merge(D_all, I_all)
+            assert all(np.array_equal(Im2[g], Io) for g in range(G))
+    finally:
+        ranks.close()
+
+
+def test_exchange_rejects_a_second_stream():
+    """Epoch double-buffering is only safe if a rank's exchanges execute in call order: the first call fixes the
+    stream, another one is an error (not a silent race)."""
+    from kirag_b200 import _lib
+
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    _lib.check(lib.kirag_exchange_create(0, 0, 1, 8, 8, ctypes.byref(h)), "create")
+    try:
+        D = torch.zeros((2, 4), device="cuda")
+        I = torch.arange(8, device="cuda").reshape(2, 4)
+        Do, Io = torch.empty_like(D), torch.empty_like(I)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        args = (ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()), 2, 4, ctypes.c_void_p(Do.data_ptr()),
+                ctypes.c_void_p(Io.data_ptr()))
+        assert lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s1.cuda_stream)) == 0
+        assert lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s2.cuda_stream)) != 0
+        assert "same stream" in _lib.last_error()
+        assert lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s1.cuda_stream)) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(Io, I)
+    finally:
+        lib.kirag_exchange_destroy(h)
 
 
 def test_exchange_rejects_bad_arguments():

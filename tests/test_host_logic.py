@@ -191,4 +191,6 @@ def test_level_schedule_reference_points():
 
 def test_level_schedule_ineligible_shapes():
     assert _schedule(1000, 4, 10, d=100)[0] == -1      # d not a multiple of 64: exact scan only
-    assert _schedule(1000, 4, 1024)[0] == -1           # k' = 4096 > 2048
+    # k > 512: the over-fetch is capped at k' = 2048, the filter path still takes it (k <= 2048)
+    n_levels, bounds, cap, kprime = _schedule(1_000_000, 4, 1024)
+    assert n_levels > 0 and kprime == 2048 and cap >= 4 * kprime and bounds[-1] == 1_000_000

@@ -354,3 +354,85 @@ def test_device_pointer_entry_points(fa):
     D, I = ix.search_device(torch.from_numpy(xq).cuda(), 10, id_offset=5)
     torch.cuda.synchronize()
     assert_topk_parity(D.cpu().numpy(), I.cpu().numpy() - 5, xb, xq, 10, what="device pointers")
+
+
+# ------------------------------------------------- asynchronous search (async + finish) ---
+def test_async_search_then_finish_equals_the_synchronous_call(fa):
+    """kirag_index_search_async enqueues the first attempt without a host synchronisation;
+    kirag_index_search_finish verifies the certificates and re-answers flagged queries in place."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    # (a) well-spread data: every certificate passes, finish() changes nothing
+    xb, xq = unit_rows(rng, 60000, 256), unit_rows(rng, 40, 256)
+    ix = build(fa, xb)
+    q = torch.from_numpy(xq).cuda()
+    Ds, Is = ix.search_device(q, 20)
+    Da, Ia = ix.search_device_async(q, 20)
+    assert ix.pending_flags_ptr() != 0
+    changed = ix.finish()
+    assert changed == 0 and ix.last_stats["n_fast"] == 40, ix.last_stats
+    assert torch.equal(Ia, Is) and torch.equal(Da, Ds)
+    assert ix.pending_flags_ptr() == 0 and ix.finish() == 0  # nothing pending any more
+    # (b) clustered data: the certificates fail, finish() rewrites those rows and the result is the exact one
+    centers = unit_rows(rng, 8, 128)
+    xc = centers[rng.integers(0, 8, 40000)] + 0.004 * rng.standard_normal((40000, 128)).astype(np.float32)
+    xc = (xc / np.linalg.norm(xc, axis=1, keepdims=True)).astype(np.float32)
+    qc = torch.from_numpy((centers[:4] + 0.01 * unit_rows(rng, 4, 128)).astype(np.float32)).cuda()
+    ic = build(fa, xc)
+    De, Ie = ic.search_device(qc, 10, path=EXACT)
+    Da, Ia = ic.search_device_async(qc, 10)
+    changed = ic.finish()
+    st = ic.last_stats
+    assert changed >= 1 and st["n_cert_fail"] >= 1 and st["n_rescan"] + st["n_exact"] == changed, st
+    assert torch.equal(Ia, Ie) and torch.equal(Da, De)
+    # (c) an unfinished asynchronous search is completed by the next call on the handle
+    Da, Ia = ic.search_device_async(qc, 10)
+    Ds2, Is2 = ic.search_device(qc[:2].contiguous(), 10)
+    torch.cuda.synchronize()
+    assert torch.equal(Ia, Ie) and torch.equal(Is2, Ie[:2])
+
+
+def test_async_search_is_cuda_graph_capturable(fa):
+    """Once the workspaces are warm the asynchronous half allocates nothing and never synchronises: it can be
+    captured into a CUDA graph and replayed on new query contents."""
+    import torch
+
+    rng = np.random.default_rng(22)
+    xb = unit_rows(rng, 80000, 128)
+    ix = build(fa, xb)
+    q = torch.from_numpy(unit_rows(rng, 8, 128)).cuda()
+    ix.search_device(q, 10)  # warm the workspaces
+    D = torch.empty((8, 10), dtype=torch.float32, device="cuda")
+    I = torch.empty((8, 10), dtype=torch.int64, device="cuda")
+    import ctypes
+
+    from kirag_b200 import _lib
+
+    lib = _lib.load()
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(graph, stream=stream):
+            _lib.check(lib.kirag_index_search_async(ix._h, ctypes.c_void_p(q.data_ptr()), 8, 10, ctypes.c_void_p(D.data_ptr()),
+                                                    ctypes.c_void_p(I.data_ptr()), 0, ctypes.c_void_p(stream.cuda_stream)),
+                       "search_async (captured)")
+    for trial in range(3):
+        q.copy_(torch.from_numpy(unit_rows(rng, 8, 128)))
+        graph.replay()
+        stream.synchronize()
+        torch.cuda.synchronize()
+        assert_topk_parity(D.cpu().numpy(), I.cpu().numpy(), xb, q.cpu().numpy(), 10, what=f"graph replay {trial}")
+    assert ix.finish() == 0  # the captured call left a pending search behind: complete it
+
+
+def test_k_above_512_stays_on_the_filter_path(fa):
+    """k' = min(4k, 2048): k up to 2048 is answered by the tcgen05 filter path, not by the fp32 scan."""
+    rng = np.random.default_rng(23)
+    xb, xq = unit_rows(rng, 150000, 128), unit_rows(rng, 3, 128)
+    ix = build(fa, xb)
+    for k in (600, 2048):
+        D, I, st = ix.search_ex(xq, k, path=AUTO)
+        assert st["levels"] >= 2 and st["n_fast"] + st["n_rescan"] + st["n_exact"] == 3, st
+        assert st["n_exact"] == 0, st
+        assert_topk_parity(D, I, xb, xq, k, what=f"k={k} {st}")

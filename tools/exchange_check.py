@@ -67,6 +67,33 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
                 print(f"    exchange {name}: {t.item() * 1e3:8.1f} us (max over {world} ranks)", flush=True)
+    # Clustered rows on ONE shard only: that rank's certificates fail, the others' pass.  The flags travel with
+    # the exchange, every rank sees the same OR word, the flagged rank re-answers and all ranks exchange again.
+    centers = torch.nn.functional.normalize(torch.randn(8, d, generator=g, device=dev), dim=1)
+    pick = torch.randint(0, 8, (n,), generator=g, device=dev)
+    xc = xb.clone()
+    c_lo, c_hi = shard_range(n, world, world - 1)
+    xc[c_lo:c_hi] = torch.nn.functional.normalize(
+        centers[pick[c_lo:c_hi]] + 0.0008 * torch.randn(c_hi - c_lo, d, generator=g, device=dev), dim=1)
+    qc = torch.nn.functional.normalize(centers[:4] + 0.002 * torch.randn(4, d, generator=g, device=dev), dim=1)
+    clustered = ShardedFlatIP(d, n, rank=rank, world_size=world, device=local, exchange="peer", max_nq=64, max_k=128)
+    clustered.add_shard(xc[lo:hi])
+    Dc, Ic = clustered.search(qc, 10)
+    st = dict(clustered.index.last_stats)
+    De, Ie = clustered.search(qc, 10, path=1)  # exact fp32 scan on every shard + the same exchange
+    same = bool(torch.equal(Ic, Ie) and torch.equal(Dc, De))
+    flagged = torch.tensor([st.get("n_cert_fail", 0) + st.get("n_overflow", 0)], device=dev)
+    allf = [torch.zeros_like(flagged) for _ in range(world)]
+    dist.all_gather(allf, flagged)
+    flag = torch.tensor([1 if same else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        per_rank = [int(x.item()) for x in allf]
+        print(f"clustered shard {world - 1}: flagged queries per rank {per_rank}; async search + flag-carrying exchange == "
+              f"exact on every rank: {bool(flag.item())}", flush=True)
+        ok = ok and per_rank[-1] > 0
+    ok = ok and bool(flag.item())
+    clustered.close()
     peer.close()
     dist.barrier()
     if rank == 0:
