@@ -73,6 +73,7 @@ typedef struct kirag_search_stats {
     int32_t path;            /* path actually taken for the bulk of the call (KIRAG_PATH_*) */
     int64_t kernel_launches; /* kernels launched by this library during the call */
     int64_t n_rescan;        /* certificate failures answered by the second bf16 pass (threshold s_k - eps) */
+    int64_t n_retry;         /* buffer overflows answered by re-running the filter path with the gentle level schedule */
 } kirag_search_stats_t;
 
 /* ---- library ---------------------------------------------------------- */

@@ -35,6 +35,7 @@ class SearchStats(ctypes.Structure):
         ("path", c_int32),
         ("kernel_launches", c_int64),
         ("n_rescan", c_int64),
+        ("n_retry", c_int64),
     ]
 
     def as_dict(self):

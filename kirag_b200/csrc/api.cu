@@ -173,10 +173,11 @@ struct FastParams {
     int kprime;
     int growth_override;  // KIRAG_LEVEL_GROWTH (0: automatic)
     int cap_override;     // KIRAG_CAND_CAP (0: automatic)
+    int first_growth_override;  // KIRAG_LEVEL1_GROWTH (0: automatic)
 };
 
 struct SearchCounters {
-    int64_t n_fast = 0, n_exact = 0, n_cert_fail = 0, n_overflow = 0, n_rescan = 0, n_changed = 0;
+    int64_t n_fast = 0, n_exact = 0, n_cert_fail = 0, n_overflow = 0, n_rescan = 0, n_retry = 0, n_changed = 0;
     int levels = 0;
 };
 
@@ -193,6 +194,7 @@ struct PendingSearch {
     cudaStream_t st = nullptr;
     long long launches0 = 0;
     SearchCounters counters;
+    FastParams fp{};
 };
 
 struct kirag_index {
@@ -204,12 +206,16 @@ struct kirag_index {
     int64_t capacity = 0;       // rows
     float* master = nullptr;    // [capacity, d] fp32
     uint8_t* shadow = nullptr;  // bf16 tiles, capacity rounded up to 128 rows (null if d % 64)
-    unsigned* maxnorm2_bits = nullptr;  // device: [0] max ||x||^2, [1] max ||x - bf16(x)||^2 (float bits)
-    float maxnorm = 0.f;                // max_j ||x_j||
-    float maxerr = 0.f;                 // max_j ||x_j - bf16(x_j)||
+    unsigned* maxnorm2_bits = nullptr;  // device: [0] max ||y||^2, [1] max ||y - bf16(y)||^2, [2] max ||x||^2 (float bits)
+    float maxnorm = 0.f;                // max_j ||y_j||, y = x - center (= x without a centre): what the shadow holds
+    float maxerr = 0.f;                 // max_j ||y_j - bf16(y_j)||
+    float maxnorm_x = 0.f;              // max_j ||x_j||
+    float* center = nullptr;            // device [d]: the shadow stores bf16(x - center); null = not centred
+    float center_norm = 0.f;
+    bool center_decided = false;
     // workspaces (grow-only)
-    DevBuf q_dev, D_dev, I_dev, qshadow, qnorm, cand, cnt, tau, overflow, flags, rescored;
-    DevBuf dense, stage_a, stage_b, qmap, qsel, qnorm2;
+    DevBuf q_dev, D_dev, I_dev, qshadow, qnorm, cand, cnt, tau, tauk, overflow, flags, rescored;
+    DevBuf dense, stage_a, stage_b, qmap, qsel, qnorm2, D_tmp, I_tmp;
     int* host_flags = nullptr;  // pinned: certificate read-back without a staging copy
     size_t host_flags_n = 0;
     PendingSearch pending;
@@ -217,6 +223,61 @@ struct kirag_index {
 };
 
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoi(v);
+}
+
+// Centring decision (once per index, when it first holds kCenterMinRows rows): c = mean of the first rows, used only
+// if it is a LARGE common component (||c||^2 >= 1/16 of the mean squared row norm).  i.i.d.-like corpora (||mean|| ~
+// 1/sqrt(n)) stay uncentred and bit-identical to an index without this feature; E5-style embeddings (random-pair
+// cosine 0.7+) get c ~ their common direction.  Any fixed c is valid — it shifts all scores of a query by <q, c> — so
+// rows added later need not share the mean for exactness, only for the certificate to stay tight.
+constexpr int64_t kCenterMinRows = 4096;
+constexpr int64_t kCenterSampleRows = 65536;
+static int decide_center(kirag_index* h, int64_t rows_available, cudaStream_t st) {
+    if (env_int("KIRAG_NO_CENTER", 0)) return 0;
+    const int d = h->d;
+    const int64_t rows = rows_available < kCenterSampleRows ? rows_available : kCenterSampleRows;
+    DevBuf sums;
+    if (sums.ensure((size_t)(d + 1) * 4)) return 1;
+    std::vector<float> host((size_t)d + 1);
+    int rc = 1;
+    do {
+        if (cudaMemsetAsync(sums.p, 0, (size_t)(d + 1) * 4, st) != cudaSuccess) break;
+        if (launch_column_sums(h->master, rows, d, sums.as<float>(), st)) break;
+        if (cudaMemcpyAsync(host.data(), sums.p, (size_t)(d + 1) * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("decide_center: reading the column sums failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        double c2 = 0.0;
+        for (int c = 0; c < d; ++c) {
+            host[(size_t)c] = (float)((double)host[(size_t)c] / (double)rows);
+            c2 += (double)host[(size_t)c] * (double)host[(size_t)c];
+        }
+        const double mean_sq = (double)host[(size_t)d] / (double)rows;
+        rc = 0;
+        if (!(c2 >= mean_sq / 16.0) || !(mean_sq > 0.0) || !(c2 == c2)) break;  // no large common component
+        rc = 1;
+        if (cudaMalloc((void**)&h->center, (size_t)d * 4) != cudaSuccess) {
+            h->center = nullptr;
+            set_error("decide_center: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (cudaMemcpyAsync(h->center, host.data(), (size_t)d * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("decide_center: uploading the centre failed");
+            break;
+        }
+        h->center_norm = (float)sqrt(c2);
+        rc = 0;
+    } while (0);
+    sums.release();
+    return rc;
+}
 
 static int index_grow(kirag_index* h, int64_t need_rows, cudaStream_t st) {
     if (need_rows <= h->capacity) return 0;
@@ -312,7 +373,7 @@ static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, 
         }
         if (launch_final(cur, cur_stride, nullptr, nullptr, cur_count, cur_count, gq, k,
                          qmap_dev ? D : D + (out_row0 + g0) * k, qmap_dev ? I : I + (out_row0 + g0) * k,
-                         id_offset, nullptr, nullptr, nullptr, 0.f, 0.f, 0, nullptr, nullptr,
+                         id_offset, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, 0, nullptr, nullptr,
                          qmap_dev ? qmap_dev + g0 : nullptr, st)) return 1;
     }
     return 0;
@@ -333,12 +394,6 @@ constexpr int64_t kQChunk = 16384;  // queries per pass of the search workspaces
 constexpr int kMaxGrowth = 32;
 
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    return atoi(v);
-}
-
 static bool fast_eligible(const kirag_index* h, int k, FastParams* fp) {
     if (!h->shadow || !scan_tc_supported(h->d)) return false;
     if (h->ntotal > 0x7fffff00LL) return false;
@@ -349,6 +404,7 @@ static bool fast_eligible(const kirag_index* h, int k, FastParams* fp) {
     fp->kprime = (int)kp;
     fp->growth_override = env_int("KIRAG_LEVEL_GROWTH", 0);
     fp->cap_override = env_int("KIRAG_CAND_CAP", 0);
+    fp->first_growth_override = env_int("KIRAG_LEVEL1_GROWTH", 0);
     if (fp->cap_override > 0 && fp->cap_override < 4 * kp) return false;
     return true;
 }
@@ -372,7 +428,12 @@ static std::vector<int64_t> level_bounds(int64_t n_tiles, int cap, const FastPar
     if (gmax > kMaxGrowth) gmax = kMaxGrowth;
     if (fp.growth_override > 0) gmax = fp.growth_override;
     if (gmax < 2) gmax = 2;
-    t = t * (gmax < 4 ? gmax : 4);
+    // growth of level 1: 4 for the normal buffer; 16 for the wide buffer of small batches, where a level costs a
+    // fixed ~40 us of launch / ramp / compaction latency and an overflow is re-answered with the gentle schedule
+    int g1 = (cap >= kWideCap) ? 16 : 4;
+    if (fp.first_growth_override > 0) g1 = fp.first_growth_override;
+    if (g1 > gmax) g1 = gmax;
+    t = t * g1;
     if (t > n_tiles) t = n_tiles;
     hi.push_back(t);
     if (t >= n_tiles) return hi;
@@ -414,10 +475,16 @@ static int64_t pick_tile_mult(int64_t n_tiles) {
 // for the fp32 evaluation of the norms themselves.
 struct CertEps { float a, b; };
 static CertEps cert_eps(const kirag_index* h) {
-    const double xn = (double)h->maxnorm, ex = (double)h->maxerr;
+    // y = fl(x - c) is what the shadow rounds to bf16 (y = x, c = 0 without a centre):
+    //   <q, x> = <q, y> + <q, c> + <q, (x - c) - y>                      |last term| <= 2^-24 Y ||q||
+    //   |<q~, y~> - <q, y>| <= E_y (||q|| + ||q - q~||) + Y ||q - q~||     (bf16 rounding of both sides)
+    //   fp32 accumulation: d 2^-22 Y ||q|| for the tensor-core dot, d 2^-22 X ||q|| for the canonical dot
+    //   <q, c> is evaluated in fp32 by one warp: error <= 64 * 2^-24 ||q|| ||c||
+    const double yn = (double)h->maxnorm, ey = (double)h->maxerr, xn = (double)h->maxnorm_x, cn = (double)h->center_norm;
+    const double acc = (double)h->d * ldexp(1.0, -22);
     CertEps e;
-    e.a = (float)((ex + (double)h->d * ldexp(1.0, -21) * xn) * 1.002);
-    e.b = (float)((xn + 2.0 * ex) * 1.002);
+    e.a = (float)((ey + acc * (yn + xn) + ldexp(1.0, -24) * yn + 64.0 * ldexp(1.0, -24) * cn) * 1.002);
+    e.b = (float)((yn + 2.0 * ey) * 1.002);
     return e;
 }
 
@@ -434,7 +501,7 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     if (scan_tc_pick(nq, d, &plan)) return 1;
     const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
     if (h->qshadow.ensure(qs_bytes)) return 1;
-    if (h->qnorm.ensure((size_t)nq * 8)) return 1;  // [nq] norms, then [nq] bf16 rounding-error norms
+    if (h->qnorm.ensure((size_t)nq * 12)) return 1;  // [nq] norms, [nq] bf16 rounding-error norms, [nq] <q, center>
     const int cap = pick_cap(fp, nq);
     if (h->cand.ensure((size_t)nq * cap * sizeof(Cand))) return 1;
     if (h->cnt.ensure((size_t)nq * 4)) return 1;
@@ -443,14 +510,20 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
     if (h->overflow.ensure((size_t)nq * 4)) return 1;
     if (h->flags.ensure((size_t)nq * 4)) return 1;
     if (h->rescored.ensure((size_t)nq * fp.kprime * 4)) return 1;
+    if (h->tauk.ensure((size_t)nq * 4)) return 1;
+    // rescoring skips candidates more than 2 eps below the k-th best approximate score (KIRAG_RESCORE_ALL=1: all k')
+    const bool skip_far = env_int("KIRAG_RESCORE_ALL", 0) == 0;
+    // small batches (wide candidate buffer): last compaction + rescoring + final sort are ONE cluster kernel
+    const bool fuse_tail = cap == kWideCap && fp.kprime <= 2048 && env_int("KIRAG_FUSED_TAIL", 1) != 0;
     if ((nq % plan.bq) != 0)  // only the pad rows of the last query tile need zeroing
         KIRAG_CUDA_OK(cudaMemsetAsync(h->qshadow.p, 0, qs_bytes, st));
     KIRAG_CUDA_OK(launch_chained(init_search_state_kernel, dim3((unsigned)((nq_pad + 255) / 256)), dim3(256), 0, st,
                                  h->tau.as<float>(), h->cnt.as<int>(), h->overflow.as<int>(), nq, nq_pad));
     KIRAG_LAUNCH_OK("init_search_state_kernel");
     prof_mark(0, st);
+    float* const qcdot = h->qnorm.as<float>() + 2 * nq;
     if (launch_convert_rows(qd, nq, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, h->qnorm.as<float>(),
-                            h->qnorm.as<float>() + nq, st)) return 1;
+                            h->qnorm.as<float>() + nq, h->center, qcdot, st)) return 1;
     prof_mark(1, st);
 
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
@@ -477,19 +550,33 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
             g_prof.queries = (double)nq;
         }
         prof_mark(10 + levels, st);
+        const bool last = (hi == bounds.back());
+        if (last && fuse_tail) break;  // the fused tail kernel below does this level's compaction itself
         if (launch_compact_topm(h->cand.as<Cand>(), cap, h->cnt.as<int>(), cap, (int)nq, fp.kprime,
-                                h->tau.as<float>(), h->overflow.as<int>(), st)) return 1;
+                                h->tau.as<float>(), h->overflow.as<int>(), (last && skip_far) ? h->tauk.as<float>() : nullptr,
+                                k, st)) return 1;
         prof_mark(30 + levels, st);
         ++levels;
         lo = hi;
     }
-    if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), cap, fp.kprime,
-                       h->rescored.as<float>(), nq, st)) return 1;
-    prof_mark(50, st);
     const CertEps ce = cert_eps(h);
+    if (fuse_tail) {
+        ++levels;
+        if (launch_tail_fused(h->cand.as<Cand>(), cap, h->cnt.as<int>(), cap, (int)nq, fp.kprime, h->tau.as<float>(),
+                              h->overflow.as<int>(), h->master, d, qd, h->rescored.as<float>(), k, D, I, id_offset,
+                              h->qnorm.as<float>(), h->qnorm.as<float>() + nq, qcdot, ce.a, ce.b, h->flags.as<int>(),
+                              h->num_sms, st)) return 1;
+        prof_mark(51, st);
+        if (levels_out) *levels_out = levels;
+        return 0;
+    }
+    if (launch_rescore(h->master, d, qd, h->cand.as<Cand>(), h->cnt.as<int>(), cap, fp.kprime,
+                       h->rescored.as<float>(), nq, skip_far ? h->tauk.as<float>() : nullptr, h->qnorm.as<float>(),
+                       h->qnorm.as<float>() + nq, ce.a, ce.b, st)) return 1;
+    prof_mark(50, st);
     if (launch_final(h->cand.as<Cand>(), cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, fp.kprime,
                      (int)nq, k, D, I, id_offset, h->tau.as<float>(), h->qnorm.as<float>(), h->qnorm.as<float>() + nq,
-                     ce.a, ce.b, check_cert, h->overflow.as<int>(), h->flags.as<int>(), nullptr, st)) return 1;
+                     qcdot, ce.a, ce.b, check_cert, h->overflow.as<int>(), h->flags.as<int>(), nullptr, st)) return 1;
     prof_mark(51, st);
     if (levels_out) *levels_out = levels;
     return 0;
@@ -498,7 +585,8 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
 // tau2[i] = (k-th canonical score of flagged query i) - eps_i : every row of the true top-k has an
 // approximate score >= tau2 (certificate); a query without k results gets -inf
 __global__ void rescan_threshold_kernel(const float* __restrict__ D, const int* __restrict__ qmap,
-                                        const float* __restrict__ qnorm, const float* __restrict__ qerr, int k,
+                                        const float* __restrict__ qnorm, const float* __restrict__ qerr,
+                                        const float* __restrict__ qcdot, int k,
                                         float eps_a, float eps_b, int64_t nb,
                                         int64_t nb_pad, float* __restrict__ tau2, int* __restrict__ cnt,
                                         int* __restrict__ overflow) {
@@ -507,7 +595,8 @@ __global__ void rescan_threshold_kernel(const float* __restrict__ D, const int* 
     if (i >= nb) { tau2[i] = INFINITY; return; }
     const int q = qmap[i];
     const float kth = D[(int64_t)q * k + (k - 1)];
-    tau2[i] = (kth > -FLT_MAX) ? kth - (eps_a * qnorm[q] + eps_b * qerr[q]) : -INFINITY;
+    // the shadow holds x - c: its scores are lower than the true ones by <q, c>
+    tau2[i] = (kth > -FLT_MAX) ? kth - (eps_a * qnorm[q] + eps_b * qerr[q]) - qcdot[q] : -INFINITY;
     cnt[i] = 0;
     overflow[i] = 0;
 }
@@ -517,7 +606,8 @@ __global__ void rescan_threshold_kernel(const float* __restrict__ D, const int* 
 // candidate is rescored in fp32.  Exact by construction; only a buffer overflow (more than `cap`
 // rows within eps of the k-th score) is left to the exact fp32 scan.  qsel: the flagged queries
 // gathered contiguously; qmap: their row numbers in D/I.  still_bad (host) receives the overflowed ones.
-static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_all, const float* qerr_all, int64_t nb,
+static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_all, const float* qerr_all,
+                         const float* qcdot_all, int64_t nb,
                          int k, float* D,
                          int64_t* I, const int* qmap_dev, int64_t id_offset, int cap, std::vector<int>* still_bad,
                          cudaStream_t st) {
@@ -535,20 +625,22 @@ static int rescan_search(kirag_index* h, const float* qsel, const float* qnorm_a
     const CertEps ce = cert_eps(h);
     // thresholds from the first-attempt results (still in D), before anything is overwritten
     rescan_threshold_kernel<<<(unsigned)((nb_pad + 255) / 256), 256, 0, st>>>(
-        D, qmap_dev, qnorm_all, qerr_all, k, ce.a, ce.b, nb, nb_pad, h->tau.as<float>(), h->cnt.as<int>(),
+        D, qmap_dev, qnorm_all, qerr_all, qcdot_all, k, ce.a, ce.b, nb, nb_pad, h->tau.as<float>(), h->cnt.as<int>(),
         h->overflow.as<int>());
     KIRAG_LAUNCH_OK("rescan_threshold_kernel");
     if ((nb % plan.bq) != 0) KIRAG_CUDA_OK(cudaMemsetAsync(h->qshadow.p, 0, qs_bytes, st));
-    if (launch_convert_rows(qsel, nb, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, nullptr, nullptr, st)) return 1;
+    if (launch_convert_rows(qsel, nb, d, 0, h->qshadow.p, plan.q_tile_rows, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            st)) return 1;
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
     if (launch_scan_tc(h->shadow, n, d, h->qshadow.p, nb, plan, 0, n_tiles, n_tiles, 1, h->tau.as<float>(),
                        h->cand.as<Cand>(), h->cnt.as<int>(), cap, h->num_sms, 1, st)) return 1;
-    if (launch_rescore(h->master, d, qsel, h->cand.as<Cand>(), h->cnt.as<int>(), cap, cap, h->rescored.as<float>(), nb, st)) return 1;
+    if (launch_rescore(h->master, d, qsel, h->cand.as<Cand>(), h->cnt.as<int>(), cap, cap, h->rescored.as<float>(), nb,
+                       nullptr, nullptr, nullptr, 0.f, 0.f, st)) return 1;
     // overflow = appended count beyond the buffer
     std::vector<int> counts((size_t)nb);
     KIRAG_CUDA_OK(cudaMemcpyAsync(counts.data(), h->cnt.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
     if (launch_final(h->cand.as<Cand>(), cap, h->rescored.as<float>(), h->cnt.as<int>(), 0, cap, (int)nb, k, D, I,
-                     id_offset, nullptr, nullptr, nullptr, 0.f, 0.f, 0, nullptr, nullptr, qmap_dev, st)) return 1;
+                     id_offset, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, 0, nullptr, nullptr, qmap_dev, st)) return 1;
     KIRAG_CUDA_OK(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < nb; ++i)
         if (counts[(size_t)i] > cap) still_bad->push_back((int)i);
@@ -594,41 +686,84 @@ static int enqueue_chunk(kirag_index* h, const float* qd, int64_t cq, int k, flo
     return 0;
 }
 
+__global__ void scatter_rows_kernel(const float* __restrict__ Ds, const int64_t* __restrict__ Is, const int* __restrict__ qmap,
+                                    int k, float* __restrict__ D, int64_t* __restrict__ I) {
+    const int64_t src = blockIdx.x, dst = qmap[src];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        D[dst * k + j] = Ds[src * k + j];
+        I[dst * k + j] = Is[src * k + j];
+    }
+}
+
 // The stream must have been synchronised since enqueue_chunk.  Returns with the stream idle.
+// Escalation ladder for the flagged queries of a chunk (KIRAG_PATH_AUTO):
+//   overflowed candidate buffer  -> the filter path once more with the gentle level schedule (growth 2, then 4):
+//                                   the first attempt's schedule is tuned for latency and bets on the sampled
+//                                   thresholds being representative; corpora clustered by position can lose that bet
+//   certificate failed           -> ONE more bf16 pass with the provable threshold s_k - eps
+//   whatever is left             -> the exact fp32 scan
 static int resolve_chunk(kirag_index* h, const float* qd, int64_t cq, int k, float* Dd, int64_t* Id, int64_t id_offset,
-                         int path, SearchCounters* c, cudaStream_t st) {
+                         int path, const FastParams& fp, SearchCounters* c, cudaStream_t st) {
     const int d = h->d;
     const int* flags = h->host_flags;
-    std::vector<char> ovf((size_t)cq);
-    std::vector<int> bad;
+    std::vector<int> cert, ovf;
     for (int64_t i = 0; i < cq; ++i) {
-        ovf[(size_t)i] = flags[(size_t)i] == 2 ? 1 : 0;
-        if (ovf[(size_t)i]) ++c->n_overflow;
-        if (flags[(size_t)i]) { bad.push_back((int)i); if (!ovf[(size_t)i]) ++c->n_cert_fail; }
+        if (flags[(size_t)i] == 2) { ovf.push_back((int)i); ++c->n_overflow; }
+        else if (flags[(size_t)i]) { cert.push_back((int)i); ++c->n_cert_fail; }
     }
-    if (bad.empty() || path != KIRAG_PATH_AUTO) {
+    const int64_t n_bad = (int64_t)(cert.size() + ovf.size());
+    if (n_bad == 0 || path != KIRAG_PATH_AUTO) {
         c->n_fast += cq;
         return 0;
     }
-    // 1st escalation: certificate failures (not overflows) get one more bf16 pass with the provable
-    // threshold; 2nd: whatever is left goes to the exact fp32 scan
-    std::vector<int> rescan, exact;
+    // the norm / flag buffers are reused below: keep the first attempt's norms (+ error norms, + <q, center>)
+    if (h->qnorm2.ensure((size_t)cq * 12)) return 1;
+    KIRAG_CUDA_OK(cudaMemcpyAsync(h->qnorm2.p, h->qnorm.p, (size_t)cq * 12, cudaMemcpyDeviceToDevice, st));
+    std::vector<int> exact;
     const bool no_rescan = env_int("KIRAG_NO_RESCAN", 0) != 0;
-    for (int b : bad) ((ovf[(size_t)b] || no_rescan) ? exact : rescan).push_back(b);
-    if (!rescan.empty()) {
-        const int64_t nb = (int64_t)rescan.size();
+    const bool gentle_already = fp.growth_override > 0 && fp.growth_override <= 4 && fp.first_growth_override > 0;
+    if (!ovf.empty() && !gentle_already && !env_int("KIRAG_NO_RETRY", 0)) {
+        const int64_t nb = (int64_t)ovf.size();
+        if (h->qmap.ensure((size_t)nb * 4) || h->qsel.ensure((size_t)nb * d * 4)) return 1;
+        if (h->D_tmp.ensure((size_t)nb * k * 4) || h->I_tmp.ensure((size_t)nb * k * 8)) return 1;
+        KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, ovf.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
+        KIRAG_LAUNCH_OK("gather_rows_kernel");
+        FastParams gentle = fp;
+        gentle.growth_override = 4;
+        gentle.first_growth_override = 2;
+        if (fast_search(h, h->qsel.as<float>(), nb, k, h->D_tmp.as<float>(), h->I_tmp.as<int64_t>(), id_offset, gentle, 1,
+                        nullptr, st)) return 1;
+        std::vector<int> f2((size_t)nb);
+        KIRAG_CUDA_OK(cudaMemcpyAsync(f2.data(), h->flags.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        scatter_rows_kernel<<<(unsigned)nb, 128, 0, st>>>(h->D_tmp.as<float>(), h->I_tmp.as<int64_t>(), h->qmap.as<int>(), k,
+                                                          Dd, Id);
+        KIRAG_LAUNCH_OK("scatter_rows_kernel");
+        KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < nb; ++i) {
+            if (f2[(size_t)i] == 0) ++c->n_retry;
+            else if (f2[(size_t)i] == 2) exact.push_back(ovf[(size_t)i]);
+            else cert.push_back(ovf[(size_t)i]);  // its rows of D now hold a valid k-th score for the rescan threshold
+        }
+    } else {
+        exact = ovf;
+    }
+    if (!cert.empty() && no_rescan) {
+        exact.insert(exact.end(), cert.begin(), cert.end());
+        cert.clear();
+    }
+    if (!cert.empty()) {
+        const int64_t nb = (int64_t)cert.size();
         if (h->qmap.ensure((size_t)nb * 4)) return 1;
         if (h->qsel.ensure((size_t)nb * d * 4)) return 1;
-        if (h->qnorm2.ensure((size_t)cq * 8)) return 1;
-        // qnorm / flags buffers are reused by the rescan: keep a copy of the norms (+ error norms)
-        KIRAG_CUDA_OK(cudaMemcpyAsync(h->qnorm2.p, h->qnorm.p, (size_t)cq * 8, cudaMemcpyDeviceToDevice, st));
-        KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, rescan.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        KIRAG_CUDA_OK(cudaMemcpyAsync(h->qmap.p, cert.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
         gather_rows_kernel<<<(unsigned)nb, 256, 0, st>>>(qd, h->qmap.as<int>(), d, h->qsel.as<float>());
         KIRAG_LAUNCH_OK("gather_rows_kernel");
         std::vector<int> still_bad;
-        if (rescan_search(h, h->qsel.as<float>(), h->qnorm2.as<float>(), h->qnorm2.as<float>() + cq, nb, k, Dd, Id,
-                          h->qmap.as<int>(), id_offset, kSelectSeg, &still_bad, st)) return 1;
-        for (int i : still_bad) exact.push_back(rescan[(size_t)i]);
+        if (rescan_search(h, h->qsel.as<float>(), h->qnorm2.as<float>(), h->qnorm2.as<float>() + cq,
+                          h->qnorm2.as<float>() + 2 * cq, nb, k, Dd, Id, h->qmap.as<int>(), id_offset, kSelectSeg, &still_bad,
+                          st)) return 1;
+        for (int i : still_bad) exact.push_back(cert[(size_t)i]);
         c->n_rescan += nb - (int64_t)still_bad.size();
     }
     if (!exact.empty()) {
@@ -641,10 +776,10 @@ static int resolve_chunk(kirag_index* h, const float* qd, int64_t cq, int k, flo
         if (exact_search(h, h->qsel.as<float>(), nb, k, Dd, Id, 0, h->qmap.as<int>(), id_offset, st)) return 1;
         c->n_exact += nb;
     }
-    // exact[] / rescan[] live on this stack frame until the copies above have been consumed
+    // the index vectors live on this stack frame until the copies above have been consumed
     KIRAG_CUDA_OK(cudaStreamSynchronize(st));
-    c->n_fast += cq - (int64_t)bad.size();
-    c->n_changed += (int64_t)bad.size();
+    c->n_fast += cq - n_bad;
+    c->n_changed += n_bad;
     return 0;
 }
 
@@ -657,6 +792,7 @@ static void fill_stats(kirag_search_stats_t* stats, int64_t nq, const SearchCoun
     stats->n_cert_fail = c.n_cert_fail;
     stats->n_overflow = c.n_overflow;
     stats->n_rescan = c.n_rescan;
+    stats->n_retry = c.n_retry;
     stats->levels = c.levels;
     stats->path = fast_ok ? path : KIRAG_PATH_EXACT;
     stats->kernel_launches = g_launches.load() - launches0;
@@ -676,7 +812,7 @@ static int finish_pending(kirag_index* h, kirag_search_stats_t* stats, int64_t* 
     if (p.ev_recorded) KIRAG_CUDA_OK(cudaEventSynchronize(h->pending_ev));
     else KIRAG_CUDA_OK(cudaStreamSynchronize(p.st));
     SearchCounters c = p.counters;
-    if (p.mode == 1 && resolve_chunk(h, p.qd, p.nq, p.k, p.Dd, p.Id, p.id_offset, p.path, &c, p.st)) return 1;
+    if (p.mode == 1 && resolve_chunk(h, p.qd, p.nq, p.k, p.Dd, p.Id, p.id_offset, p.path, p.fp, &c, p.st)) return 1;
     fill_stats(stats, p.nq, c, p.fast_ok, p.path, p.launches0);
     if (n_changed) *n_changed = c.n_changed;
     return 0;
@@ -726,7 +862,7 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
         if (mode == 1 || !ptrs_are_device) KIRAG_CUDA_OK(cudaStreamSynchronize(st));
         if (mode == 1) {
             const int64_t changed0 = c.n_changed;
-            if (resolve_chunk(h, qd, cq, k, Dd, Id, id_offset, path, &c, st)) return 1;
+            if (resolve_chunk(h, qd, cq, k, Dd, Id, id_offset, path, fp, &c, st)) return 1;
             if (!ptrs_are_device && c.n_changed != changed0) {  // some rows were re-answered: fetch them again
                 KIRAG_CUDA_OK(cudaMemcpyAsync(D + q0 * k, Dd, (size_t)cq * k * 4, cudaMemcpyDeviceToHost, st));
                 KIRAG_CUDA_OK(cudaMemcpyAsync(I + q0 * k, Id, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, st));
@@ -839,7 +975,7 @@ int kirag_index_create(int d, int metric, int device, kirag_index_t** out) {
     h->metric = metric;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
-    if (cudaMalloc((void**)&h->maxnorm2_bits, 8) != cudaSuccess || cudaMemset(h->maxnorm2_bits, 0, 8) != cudaSuccess) {
+    if (cudaMalloc((void**)&h->maxnorm2_bits, 12) != cudaSuccess || cudaMemset(h->maxnorm2_bits, 0, 12) != cudaSuccess) {
         set_error("index_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete h;
         return 1;
@@ -855,8 +991,10 @@ int kirag_index_destroy(kirag_index_t* h) {
     if (h->master) cudaFree(h->master);
     if (h->shadow) cudaFree(h->shadow);
     if (h->maxnorm2_bits) cudaFree(h->maxnorm2_bits);
-    DevBuf* bufs[] = {&h->q_dev, &h->D_dev, &h->I_dev, &h->qshadow, &h->qnorm, &h->cand, &h->cnt, &h->tau,
-                      &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel, &h->qnorm2};
+    if (h->center) cudaFree(h->center);
+    DevBuf* bufs[] = {&h->q_dev, &h->D_dev, &h->I_dev, &h->qshadow, &h->qnorm, &h->cand, &h->cnt, &h->tau, &h->tauk,
+                      &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel, &h->qnorm2,
+                      &h->D_tmp, &h->I_tmp};
     for (DevBuf* b : bufs) b->release();
     if (h->host_flags) cudaFreeHost(h->host_flags);
     if (h->pending_ev) cudaEventDestroy(h->pending_ev);
@@ -886,14 +1024,26 @@ int kirag_index_add(kirag_index_t* h, const float* x, int64_t n, int x_is_device
     float* dst = h->master + h->ntotal * (int64_t)h->d;
     KIRAG_CUDA_OK(cudaMemcpyAsync(dst, x, (size_t)n * h->d * sizeof(float),
                                   x_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    if (launch_convert_rows(dst, n, h->d, h->ntotal, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, nullptr, st)) return 1;
-    unsigned bits[2] = {0, 0};
-    KIRAG_CUDA_OK(cudaMemcpyAsync(bits, h->maxnorm2_bits, 8, cudaMemcpyDeviceToHost, st));
+    if (h->shadow && !h->center_decided && h->ntotal + n >= kCenterMinRows) {
+        // first time the index is large enough to tell: does the corpus have a large common component?
+        if (decide_center(h, h->ntotal + n, st)) return 1;
+        h->center_decided = true;
+        if (h->center && h->ntotal > 0) {  // rows converted before the decision: once more, now centred
+            KIRAG_CUDA_OK(cudaMemsetAsync(h->maxnorm2_bits, 0, 8, st));  // [0], [1] restart; [2] (max ||x||^2) stays
+            if (launch_convert_rows(h->master, h->ntotal, h->d, 0, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, nullptr,
+                                    h->center, nullptr, st)) return 1;
+        }
+    }
+    if (launch_convert_rows(dst, n, h->d, h->ntotal, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, nullptr, h->center,
+                            nullptr, st)) return 1;
+    unsigned bits[3] = {0, 0, 0};
+    KIRAG_CUDA_OK(cudaMemcpyAsync(bits, h->maxnorm2_bits, 12, cudaMemcpyDeviceToHost, st));
     KIRAG_CUDA_OK(cudaStreamSynchronize(st));
-    float m2[2];
-    memcpy(m2, bits, 8);
+    float m2[3];
+    memcpy(m2, bits, 12);
     h->maxnorm = sqrtf(m2[0]);
     h->maxerr = h->shadow ? sqrtf(m2[1]) : 0.f;
+    h->maxnorm_x = h->shadow ? sqrtf(m2[2]) : h->maxnorm;
     h->ntotal += n;
     return 0;
 }
@@ -928,10 +1078,9 @@ int kirag_index_search_async(kirag_index_t* h, const float* q, int64_t nq, int k
     PendingSearch& p = h->pending;
     p = PendingSearch();
     p.launches0 = g_launches.load();
-    FastParams fp{};
-    p.fast_ok = h->ntotal > 0 && fast_eligible(h, k, &fp);
+    p.fast_ok = h->ntotal > 0 && fast_eligible(h, k, &p.fp);
     p.path = KIRAG_PATH_AUTO;
-    if (enqueue_chunk(h, q, nq, k, D, I, id_offset, p.fast_ok, fp, &p.counters, &p.mode, st)) return 1;
+    if (enqueue_chunk(h, q, nq, k, D, I, id_offset, p.fast_ok, p.fp, &p.counters, &p.mode, st)) return 1;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     if (cap == cudaStreamCaptureStatusNone) {
@@ -996,9 +1145,11 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
     }
     const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);
     const int64_t nq_pad = round_up(nq, 256);
-    DevBuf qd, qs, tau, cnt, dump;
+    DevBuf qd, qs, tau, cnt, dump, cdot;
+    std::vector<float> cdot_host;
     int rc = 1;
     do {
+        if (cdot.ensure((size_t)nq_pad * 4)) break;
         if (qd.ensure((size_t)nq * d * 4) || qs.ensure(qs_bytes) || tau.ensure((size_t)nq_pad * 4) ||
             cnt.ensure((size_t)nq_pad * 4) || dump.ensure((size_t)h->ntotal * nq * 4)) break;
         if (cudaMemcpyAsync(qd.p, q_host, (size_t)nq * d * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
@@ -1006,17 +1157,26 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
         if (cudaMemsetAsync(cnt.p, 0, (size_t)nq_pad * 4, st) != cudaSuccess) break;
         if (cudaMemsetAsync(dump.p, 0, (size_t)h->ntotal * nq * 4, st) != cudaSuccess) break;
         if (fill_f32(tau.as<float>(), INFINITY, nq_pad, st)) break;
-        if (launch_convert_rows(qd.as<float>(), nq, d, 0, qs.p, plan.q_tile_rows, nullptr, nullptr, nullptr, st)) break;
+        if (launch_convert_rows(qd.as<float>(), nq, d, 0, qs.p, plan.q_tile_rows, nullptr, nullptr, nullptr, h->center,
+                                h->center ? cdot.as<float>() : nullptr, st)) break;
         if (launch_scan_tc_dump(h->shadow, h->ntotal, d, qs.p, nq, plan, tau.as<float>(), cnt.as<int>(),
                                 dump.as<float>(), nq, h->num_sms, st)) break;
+        if (h->center) {
+            cdot_host.resize((size_t)nq);
+            if (cudaMemcpyAsync(cdot_host.data(), cdot.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        }
         if (cudaMemcpyAsync(out_host, dump.p, (size_t)h->ntotal * nq * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) {
             set_error("debug_scores: copy/sync failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
+        // a centred shadow scores <q, x - c>: add <q, c> back so that the hook reports approximations of <q, x>
+        if (h->center)
+            for (int64_t r = 0; r < h->ntotal; ++r)
+                for (int64_t qi = 0; qi < nq; ++qi) out_host[r * nq + qi] += cdot_host[(size_t)qi];
         rc = 0;
     } while (0);
-    qd.release(); qs.release(); tau.release(); cnt.release(); dump.release();
+    qd.release(); qs.release(); tau.release(); cnt.release(); dump.release(); cdot.release();
     return rc;
 }
 
@@ -1035,6 +1195,7 @@ int kirag_debug_level_schedule(int64_t n_rows, int64_t nq, int k, int d, int64_t
     fp.kprime = (int)kp;
     fp.growth_override = env_int("KIRAG_LEVEL_GROWTH", 0);
     fp.cap_override = env_int("KIRAG_CAND_CAP", 0);
+    fp.first_growth_override = env_int("KIRAG_LEVEL1_GROWTH", 0);
     if (fp.cap_override > 0 && fp.cap_override < 4 * kp) return -1;
     const int cap = pick_cap(fp, nq);
     const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
@@ -1205,8 +1366,10 @@ int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d,
     if (finish_pending(h, nullptr, nullptr)) return 1;
     // forget the previous call's rows (capacity and workspaces stay)
     h->ntotal = 0;
-    h->maxnorm = h->maxerr = 0.f;
-    KIRAG_CUDA_OK(cudaMemsetAsync(h->maxnorm2_bits, 0, 8, st));
+    h->maxnorm = h->maxerr = h->maxnorm_x = h->center_norm = 0.f;
+    h->center_decided = false;
+    if (h->center) { cudaFree(h->center); h->center = nullptr; }
+    KIRAG_CUDA_OK(cudaMemsetAsync(h->maxnorm2_bits, 0, 12, st));
     int rc = 0;
     if (nt > 0) rc = kirag_index_add(h, t, nt, ptrs_are_device, stream);
     if (!rc) rc = kirag_index_search(h, q, nq, k, D, I, ptrs_are_device, 0, stream);

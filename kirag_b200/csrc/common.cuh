@@ -193,16 +193,23 @@ __device__ __forceinline__ float warp_butterfly_sum(float v) {
 
 // ------------------------------------------------------ kernel launchers ---
 // convert.cu
+// center: corpus rows are stored as bf16(x - center) (row_cdot == nullptr); for query rows pass row_cdot to get
+// <q, center> per row instead (the rows themselves are converted unshifted)
 int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row0, void* shadow,
                         int rows_per_tile, unsigned* maxnorm2_bits, float* row_norms, float* row_errs,
-                        cudaStream_t st);
+                        const float* center, float* row_cdot, cudaStream_t st);
+// sums[0..d) += column sums of rows [0, n_rows), sums[d] += sum of squared elements
+int launch_column_sums(const float* src, int64_t n_rows, int d, float* sums, cudaStream_t st);
 // scan_exact.cu
 constexpr int kExactNQ = 4;
 int launch_scan_exact(const float* master, int64_t n, int d, const float* q, int nq_valid,
                       float* scores, int64_t ld, int num_sms, cudaStream_t st);
 // rescore.cu
+// tauk / qnorm / qerr (optional): candidates whose approximate score is below tauk[q] - 2 (eps_a |q| + eps_b |q - q~|)
+// are not rescored (their slot gets NaN = absent)
 int launch_rescore(const float* master, int d, const float* q, const Cand* cand, const int* cnt,
-                   int cand_stride, int m, float* out_scores, int64_t nq, cudaStream_t st);
+                   int cand_stride, int m, float* out_scores, int64_t nq, const float* tauk, const float* qnorm,
+                   const float* qerr, float eps_a, float eps_b, cudaStream_t st);
 // select.cu
 constexpr int kSelectSeg = 8192;
 constexpr int kWideCap = 32768;  // candidate buffer of small query batches (fewer, longer levels)
@@ -211,12 +218,18 @@ int launch_select_dense(const float* scores, int64_t ld, int64_t n, int nq, int 
 int launch_select_pairs(const Cand* in, int64_t in_stride, const int* cnt, int fixed_count, int cap,
                         int nq, int m, Cand* out, int64_t out_stride, int n_seg, float* tau,
                         int* cnt_out, int* overflow, cudaStream_t st);
+// tauk (optional, last level): receives the kth_k-th best approximate score among the kept candidates (-inf if fewer)
 int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, int m, float* tau, int* overflow,
-                        cudaStream_t st);
+                        float* tauk, int kth_k, cudaStream_t st);
+// last compaction + fp32 rescoring + final sort + certificate in ONE cluster kernel (small query batches)
+int launch_tail_fused(Cand* buf, int64_t stride, int* cnt, int cap, int nq, int m, float* tau, int* overflow,
+                      const float* master, int d, const float* q, float* rescored, int k, float* D, int64_t* I,
+                      int64_t id_offset, const float* qnorm, const float* qerr, const float* qcdot, float eps_a, float eps_b,
+                      int* flags, int num_sms, cudaStream_t st);
 int launch_final(const Cand* cand, int64_t cand_stride, const float* rescored, const int* cnt,
                  int fixed_count, int m_in, int nq, int k, float* D, int64_t* I, int64_t id_offset,
-                 const float* tau, const float* qnorm, const float* qerr, float eps_a, float eps_b, int check_cert,
-                 const int* overflow, int* flags, const int* qmap, cudaStream_t st);
+                 const float* tau, const float* qnorm, const float* qerr, const float* qcdot, float eps_a, float eps_b,
+                 int check_cert, const int* overflow, int* flags, const int* qmap, cudaStream_t st);
 int launch_merge(const float* D_all, const int64_t* I_all, int G, int64_t nq, int k, float* D_out,
                  int64_t* I_out, cudaStream_t st);
 int launch_fill_pad(float* D, int64_t* I, int64_t n, cudaStream_t st);

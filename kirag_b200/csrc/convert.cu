@@ -13,11 +13,18 @@ namespace kirag {
 // columns each): reads 32 contiguous bytes of fp32, writes 16 bytes of bf16.
 // A warp therefore reads 1 KB contiguous per step and fills whole 128-byte
 // swizzle rows.  HBM-bound: 4 B read + 2 B written per element.
+//
+// `center` (optional, corpus rows only): the shadow stores bf16(x - c) for a fixed vector c.  Subtracting a
+// constant vector from every corpus row shifts all scores of a query by the constant <q, c>, so the ranking the
+// filter works on is unchanged, while the bf16 rounding error now scales with ||x - c|| instead of ||x||: on
+// embeddings with a large common component (E5: random-pair cosine 0.7+) that is what keeps the exactness
+// certificate passing (api.cu::cert_eps).  maxnorm2_bits: [0] max ||y||^2, [1] max ||y - bf16(y)||^2 with
+// y = fl(x - c) (y = x without a centre), [2] max ||x||^2.
 __global__ void __launch_bounds__(256)
 convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_t dst_row0,
                     uint8_t* __restrict__ shadow, int rows_per_tile,
                     unsigned* __restrict__ maxnorm2_bits, float* __restrict__ row_norms,
-                    float* __restrict__ row_errs) {
+                    float* __restrict__ row_errs, const float* __restrict__ center, float* __restrict__ row_cdot) {
     pdl_wait();
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
@@ -26,11 +33,26 @@ convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_
     const int n_gran = d >> 3;
     for (int64_t r = warp; r < n_rows; r += n_warps) {
         const float* row = src + r * (int64_t)d;
-        float ss = 0.0f;
+        float ss = 0.0f;  // ||y||^2
+        float xs = 0.0f;  // ||x||^2 (differs from ss only with a centre)
         float es = 0.0f;  // squared norm of the bf16 rounding error of this row (exact differences, fp32 sum)
+        float cd = 0.0f;  // <x, c> (queries: the score offset the centred shadow leaves out)
         for (int g = lane; g < n_gran; g += 32) {
-            const float4 a = *reinterpret_cast<const float4*>(row + g * 8);
-            const float4 b = *reinterpret_cast<const float4*>(row + g * 8 + 4);
+            float4 a = *reinterpret_cast<const float4*>(row + g * 8);
+            float4 b = *reinterpret_cast<const float4*>(row + g * 8 + 4);
+            if (center) {
+                const float4 ca = __ldg(reinterpret_cast<const float4*>(center + g * 8));
+                const float4 cb = __ldg(reinterpret_cast<const float4*>(center + g * 8 + 4));
+                if (row_cdot) {  // query side: the row itself is NOT shifted, only <q, c> is wanted
+                    cd = fmaf(a.x, ca.x, cd); cd = fmaf(a.y, ca.y, cd); cd = fmaf(a.z, ca.z, cd); cd = fmaf(a.w, ca.w, cd);
+                    cd = fmaf(b.x, cb.x, cd); cd = fmaf(b.y, cb.y, cd); cd = fmaf(b.z, cb.z, cd); cd = fmaf(b.w, cb.w, cd);
+                } else {
+                    xs = fmaf(a.x, a.x, xs); xs = fmaf(a.y, a.y, xs); xs = fmaf(a.z, a.z, xs); xs = fmaf(a.w, a.w, xs);
+                    xs = fmaf(b.x, b.x, xs); xs = fmaf(b.y, b.y, xs); xs = fmaf(b.z, b.z, xs); xs = fmaf(b.w, b.w, xs);
+                    a.x = __fsub_rn(a.x, ca.x); a.y = __fsub_rn(a.y, ca.y); a.z = __fsub_rn(a.z, ca.z); a.w = __fsub_rn(a.w, ca.w);
+                    b.x = __fsub_rn(b.x, cb.x); b.y = __fsub_rn(b.y, cb.y); b.z = __fsub_rn(b.z, cb.z); b.w = __fsub_rn(b.w, cb.w);
+                }
+            }
             ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss);
             ss = fmaf(a.z, a.z, ss); ss = fmaf(a.w, a.w, ss);
             ss = fmaf(b.x, b.x, ss); ss = fmaf(b.y, b.y, ss);
@@ -58,20 +80,45 @@ convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int d, int64_
         }
         ss = warp_butterfly_sum(ss);
         es = warp_butterfly_sum(es);
+        if (center && !row_cdot) xs = warp_butterfly_sum(xs); else xs = ss;
+        if (row_cdot) cd = warp_butterfly_sum(cd);
         if (lane == 0) {
             if (row_norms) row_norms[r] = sqrtf(ss);
             if (row_errs) row_errs[r] = (es == es) ? sqrtf(es) : INFINITY;
+            if (row_cdot) row_cdot[r] = center ? cd : 0.0f;
             // non-negative floats order like their bit patterns; NaN/inf norms
             // saturate the bound (certificate then always fails -> exact path).
-            // [0] = max ||x||^2, [1] = max ||x - bf16(x)||^2
             if (maxnorm2_bits) {
                 unsigned bits = (ss == ss) ? __float_as_uint(ss) : 0x7f800000u;
                 atomicMax(maxnorm2_bits, bits);
                 unsigned ebits = (es == es) ? __float_as_uint(es) : 0x7f800000u;
                 atomicMax(maxnorm2_bits + 1, ebits);
+                unsigned xbits = (xs == xs) ? __float_as_uint(xs) : 0x7f800000u;
+                atomicMax(maxnorm2_bits + 2, xbits);
             }
         }
     }
+}
+
+// Column sums of rows [0, n_rows) (+ the sum of squared row norms in sums[d]): the centring decision of an index
+// (api.cu::decide_center).  One block per slab of rows, one thread per column group; fp32 atomics into sums.
+__global__ void __launch_bounds__(256)
+column_sums_kernel(const float* __restrict__ src, int64_t n_rows, int d, int rows_per_block, float* __restrict__ sums) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > n_rows) r1 = n_rows;
+    float sq = 0.0f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        float acc = 0.0f;
+        for (int64_t r = r0; r < r1; ++r) {
+            const float v = src[r * (int64_t)d + c];
+            acc += v;
+            sq = fmaf(v, v, sq);
+        }
+        atomicAdd(sums + c, acc);
+    }
+    sq = warp_butterfly_sum(sq);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sums + d, sq);
 }
 
 // Row norms only (d not a multiple of 64: no shadow, exact path only).
@@ -96,9 +143,18 @@ row_norms_kernel(const float* __restrict__ src, int64_t n_rows, int d,
     }
 }
 
+int launch_column_sums(const float* src, int64_t n_rows, int d, float* sums, cudaStream_t st) {
+    if (n_rows <= 0) return 0;
+    const int rows_per_block = 64;
+    column_sums_kernel<<<(unsigned)((n_rows + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(src, n_rows, d,
+                                                                                                    rows_per_block, sums);
+    KIRAG_LAUNCH_OK("column_sums_kernel");
+    return 0;
+}
+
 int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row0, void* shadow,
                         int rows_per_tile, unsigned* maxnorm2_bits, float* row_norms, float* row_errs,
-                        cudaStream_t st) {
+                        const float* center, float* row_cdot, cudaStream_t st) {
     if (n_rows <= 0) return 0;
     const int threads = 256;
     const int64_t warps_needed = n_rows;
@@ -107,7 +163,8 @@ int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row
     if (shadow) {
         KIRAG_CHECK(d % 64 == 0, "convert: d=%d is not a multiple of 64", d);
         KIRAG_CUDA_OK(launch_chained(convert_rows_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, src, n_rows, d,
-                                     dst_row0, (uint8_t*)shadow, rows_per_tile, maxnorm2_bits, row_norms, row_errs));
+                                     dst_row0, (uint8_t*)shadow, rows_per_tile, maxnorm2_bits, row_norms, row_errs, center,
+                                     row_cdot));
         KIRAG_LAUNCH_OK("convert_rows_kernel");
     } else {
         row_norms_kernel<<<(unsigned)blocks, threads, 0, st>>>(src, n_rows, d, maxnorm2_bits,

@@ -15,7 +15,8 @@ namespace kirag {
 __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ master, int d, const float* __restrict__ q,
                const Cand* __restrict__ cand, const int* __restrict__ cnt, int cand_stride, int m,
-               float* __restrict__ out, int64_t nq, bool vec4) {
+               float* __restrict__ out, int64_t nq, bool vec4, const float* __restrict__ tauk,
+               const float* __restrict__ qnorm, const float* __restrict__ qerr, float eps_a, float eps_b) {
     pdl_wait();
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
@@ -27,8 +28,12 @@ rescore_kernel(const float* __restrict__ master, int d, const float* __restrict_
     if (count > m) count = m;
     float result = __int_as_float(0x7fc00000);  // NaN marks an empty slot
     if (j < count) {
-        const int32_t row = cand[qi * (int64_t)cand_stride + j].id;
-        if (row >= 0) {
+        const Cand cd = cand[qi * (int64_t)cand_stride + j];
+        const int32_t row = cd.id;
+        // a candidate this far below the k-th best approximate score cannot reach the top-k (select.cu, tauk)
+        bool needed = true;
+        if (tauk) needed = cd.s >= __ldcg(tauk + qi) - 2.0f * (eps_a * __ldcg(qnorm + qi) + eps_b * __ldcg(qerr + qi));
+        if (row >= 0 && needed) {
             const float* x = master + (int64_t)row * d;
             const float part = canonical_partial(x, q + qi * (int64_t)d, d, lane, vec4);
             result = warp_butterfly_sum(part);
@@ -38,7 +43,8 @@ rescore_kernel(const float* __restrict__ master, int d, const float* __restrict_
 }
 
 int launch_rescore(const float* master, int d, const float* q, const Cand* cand, const int* cnt,
-                   int cand_stride, int m, float* out_scores, int64_t nq, cudaStream_t st) {
+                   int cand_stride, int m, float* out_scores, int64_t nq, const float* tauk, const float* qnorm,
+                   const float* qerr, float eps_a, float eps_b, cudaStream_t st) {
     if (nq <= 0 || m <= 0) return 0;
     const int threads = 256;
     const int64_t warps = nq * m;
@@ -47,7 +53,7 @@ int launch_rescore(const float* master, int d, const float* q, const Cand* cand,
     const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(master) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
     KIRAG_CUDA_OK(launch_chained(rescore_kernel, dim3((unsigned)blocks), dim3(threads), 0, st, master, d, q, cand, cnt,
-                                 cand_stride, m, out_scores, nq, vec4));
+                                 cand_stride, m, out_scores, nq, vec4, tauk, qnorm, qerr, eps_a, eps_b));
     KIRAG_LAUNCH_OK("rescore_kernel");
     return 0;
 }

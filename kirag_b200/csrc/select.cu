@@ -197,7 +197,8 @@ __device__ __forceinline__ int radix_pass(CompactSmem& sm, int which, int& kk, i
 template <int NS, int THREADS>
 __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q, int raw, int count, int cap, int m,
                                                   int* __restrict__ cnt, float* __restrict__ tau,
-                                                  int* __restrict__ overflow, CompactSmem& sm) {
+                                                  int* __restrict__ overflow, float* __restrict__ tauk, int kth_k,
+                                                  CompactSmem& sm) {
     uint32_t sk[NS];  // score key, 0 = absent (NaN score / empty slot)
     uint32_t ik[NS];  // 0xffffffff - row: larger = lower row = better
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -228,13 +229,14 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
     const int valid = sm.s_valid;
     const int keep = valid < m ? valid : m;
     uint32_t spiv = 0u, ipiv = 0u;  // keep rule: sk > spiv || (sk == spiv && ik >= ipiv); (0,0) keeps every valid item
-    if (valid > m) {
-        const unsigned all_and = sm.s_and, differ = sm.s_and ^ sm.s_or;
-        int kk = m;
-        int n_eq = valid;               // items tied with the pivot prefix decided so far
+    int which = 0;
+    const unsigned all_and = sm.s_and, differ = sm.s_and ^ sm.s_or;
+    // MSB-first radix selection of the kk-th largest SCORE key among the items selected by `in_set`; n_eq = number
+    // of set members tied at that key, kk = rank still to be resolved among them.  Bits above the highest bit in
+    // which the valid keys differ are shared by every key (all_and) and need no pass.
+    auto select_key = [&](auto in_set, int& kk, int& n_eq) -> uint32_t {
         int pos = 32 - __clz(differ);   // undecided low bits (0 if every key is the same)
-        uint32_t prefix = (pos >= 32) ? 0u : (all_and >> pos) << pos;  // bits above `pos` are shared by every key
-        int which = 0;
+        uint32_t prefix = (pos >= 32) ? 0u : (all_and >> pos) << pos;
         while (pos > 0) {
             const int w = pos < 8 ? pos : 8;
             const int shift = pos - w;
@@ -242,13 +244,19 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
             const int ppos = pos;
             const int d = radix_pass<NS>(
                 sm, which, kk, n_eq,
-                [&](int e) { return sk[e] != 0u && ((ppos >= 32) ? 0u : (sk[e] >> ppos)) == hi; },
+                [&](int e) { return in_set(e) && ((ppos >= 32) ? 0u : (sk[e] >> ppos)) == hi; },
                 [&](int e) { return (int)((sk[e] >> shift) & ((1u << w) - 1u)); });
             which ^= 1;
             prefix |= (uint32_t)d << shift;
             pos = shift;
         }
-        spiv = prefix;  // score key of the m-th best; kk of the n_eq items tied at spiv are kept
+        return prefix;
+    };
+    if (valid > m) {
+        int kk = m;
+        int n_eq = valid;               // items tied with the pivot prefix decided so far
+        spiv = select_key([&](int e) { return sk[e] != 0u; }, kk, n_eq);
+        // score key of the m-th best; kk of the n_eq items tied at spiv are kept
         if (n_eq > kk) {  // ties straddle rank m: the kk lowest rows among them win
             uint32_t ipre = 0u;
             int n_in = n_eq;
@@ -264,6 +272,19 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
             }
             ipiv = ipre;
         }
+    }
+    // Last level only (tauk != nullptr): the kth_k-th best APPROXIMATE score among the kept candidates.  Rescoring
+    // then skips every candidate whose approximate score is below tauk - 2 eps: at least kth_k candidates have a
+    // canonical score >= tauk - eps, the skipped ones have one < tauk - eps, so none of them can be in the top-k.
+    if (tauk) {
+        float tk = -INFINITY;
+        if (keep >= kth_k) {  // block-uniform
+            int kk = kth_k, n_eq = keep;
+            const uint32_t key = select_key(
+                [&](int e) { return sk[e] != 0u && (sk[e] > spiv || (sk[e] == spiv && ik[e] >= ipiv)); }, kk, n_eq);
+            tk = key_score(key);
+        }
+        if (threadIdx.x == 0) tauk[q] = tk;
     }
     // compaction of the kept items back to the front of the list
     int mine = 0;
@@ -311,7 +332,7 @@ __device__ __forceinline__ void compact_topm_body(Cand* __restrict__ list, int q
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cnt, int cap, int m,
-                    float* __restrict__ tau, int* __restrict__ overflow) {
+                    float* __restrict__ tau, int* __restrict__ overflow, float* __restrict__ tauk, int kth_k) {
     __shared__ CompactSmem sm;
     pdl_wait();
     pdl_launch_dependents();
@@ -320,7 +341,7 @@ compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cn
     const int count = raw > cap ? cap : raw;
     const int n_slots = (count + THREADS - 1) / THREADS;  // block-uniform
     Cand* list = buf + (int64_t)q * stride;
-#define KIRAG_COMPACT_CASE(NS) compact_topm_body<NS, THREADS>(list, q, raw, count, cap, m, cnt, tau, overflow, sm)
+#define KIRAG_COMPACT_CASE(NS) compact_topm_body<NS, THREADS>(list, q, raw, count, cap, m, cnt, tau, overflow, tauk, kth_k, sm)
     if (n_slots <= 2) KIRAG_COMPACT_CASE(2);
     else if (n_slots <= 4) KIRAG_COMPACT_CASE(4);
     else if (n_slots <= 8) KIRAG_COMPACT_CASE(8);
@@ -339,11 +360,55 @@ compact_topm_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cn
 //   eps_b * ||q - bf16(q)|| (api.cu::CertEps: the corpus-side maxima are folded
 //   into eps_a / eps_b).  If the k-th canonical
 //   score exceeds tau[q] + eps, no dropped row can enter the top-k.
+// items[0..P) hold the packed (canonical score, row) pairs of query q (0 = absent); sorts them, writes row qo of
+// D / I and evaluates the certificate.  Called by all threads of a CTA.
+__device__ __forceinline__ void final_body(uint64_t* items, int P, int q, int64_t qo, int k, float* __restrict__ D,
+                                           int64_t* __restrict__ I, int64_t id_offset, const float* __restrict__ tau,
+                                           const float* __restrict__ qnorm, const float* __restrict__ qerr,
+                                           const float* __restrict__ qcdot, float eps_a,
+                                           float eps_b, int check_cert, const int* __restrict__ overflow,
+                                           int* __restrict__ flags) {
+    bitonic_sort_desc(items, P);
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        float s = -FLT_MAX;
+        int64_t id = -1;
+        if (j < P && item_key(items[j]) != 0u) {
+            s = key_score(item_key(items[j]));
+            id = (int64_t)item_id(items[j]) + id_offset;
+        }
+        D[qo * k + j] = s;
+        I[qo * k + j] = id;
+    }
+    if (threadIdx.x == 0 && flags) {
+        int fail = 0;  // 0 ok, 1 certificate failed, 2 candidate buffer overflowed
+        const bool ovf = overflow && __ldcg(overflow + q);
+        if (check_cert && tau) {
+            const float t = __ldcg(tau + q);
+            if (t > -INFINITY) {
+                // something may have been dropped: need k valid results whose
+                // k-th score clears the dropped bound
+                if (k > P || item_key(items[k - 1]) == 0u) {
+                    fail = 1;
+                } else {
+                    // tau lives in the domain of the (possibly centred) shadow: a dropped row's true score is at
+                    // most tau + <q, c> + eps
+                    const float kth = key_score(item_key(items[k - 1]));
+                    const float eps = eps_a * qnorm[q] + eps_b * qerr[q];
+                    const float shift = qcdot ? qcdot[q] : 0.0f;
+                    if (!(kth - eps > t + shift)) fail = 1;
+                }
+            }
+        }
+        flags[q] = ovf ? 2 : fail;
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __restrict__ rescored,
              const int* __restrict__ cnt, int fixed_count, int m_in, int k, float* __restrict__ D,
              int64_t* __restrict__ I, int64_t id_offset, const float* __restrict__ tau,
-             const float* __restrict__ qnorm, const float* __restrict__ qerr, float eps_a, float eps_b, int check_cert,
+             const float* __restrict__ qnorm, const float* __restrict__ qerr, const float* __restrict__ qcdot,
+             float eps_a, float eps_b, int check_cert,
              const int* __restrict__ overflow, int* __restrict__ flags,
              const int* __restrict__ qmap) {
     extern __shared__ uint64_t items[];
@@ -364,37 +429,87 @@ final_kernel(const Cand* __restrict__ cand, int64_t cand_stride, const float* __
         items[i] = it;
     }
     __syncthreads();
-    bitonic_sort_desc(items, P);
     const int64_t qo = qmap ? qmap[q] : q;
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        float s = -FLT_MAX;
-        int64_t id = -1;
-        if (j < P && item_key(items[j]) != 0u) {
-            s = key_score(item_key(items[j]));
-            id = (int64_t)item_id(items[j]) + id_offset;
-        }
-        D[qo * k + j] = s;
-        I[qo * k + j] = id;
+    final_body(items, P, q, qo, k, D, I, id_offset, tau, qnorm, qerr, qcdot, eps_a, eps_b, check_cert, overflow, flags);
+}
+
+// ---- fused tail of a small-batch search --------------------------------------------------
+// Small query batches are latency-bound: last compaction, rescoring and the final sort are three dependent launches
+// of a few microseconds each.  Here ONE kernel does all three, a thread-block cluster of C CTAs per query:
+//   phase 1 (CTA 0)   exact top-k' selection of the candidate buffer (compact_topm_body)
+//   phase 2 (all C)   fp32 rescoring of the k' survivors from the master, one warp per candidate, spread over the
+//                     C SMs of the cluster (a single SM cannot pull 400 rows x 4 KB quickly)
+//   phase 3 (CTA 0)   sort by (canonical score desc, row asc), write D / I, certificate
+// The phases are separated by cluster barriers with release / acquire semantics; what crosses CTAs (the compacted
+// list, the rescored scores) goes through global memory and is read with L2 loads.
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+constexpr int kTailMaxM = 2048;
+
+__global__ void __launch_bounds__(kCompactThreadsWide, 1)
+tail_fused_kernel(Cand* __restrict__ buf, int64_t stride, int* __restrict__ cnt, int cap, int m,
+                  float* __restrict__ tau, int* __restrict__ overflow, const float* __restrict__ master, int d,
+                  const float* __restrict__ qmat, int vec4, float* __restrict__ rescored, int k,
+                  float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset, const float* __restrict__ qnorm,
+                  const float* __restrict__ qerr, const float* __restrict__ qcdot, float eps_a, float eps_b,
+                  int* __restrict__ flags) {
+    __shared__ CompactSmem sm;
+    __shared__ uint64_t items[kTailMaxM];
+    uint32_t crank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    pdl_wait();
+    pdl_launch_dependents();
+    const int q = blockIdx.x / csize;
+    Cand* list = buf + (int64_t)q * stride;
+    if (crank == 0) {
+        const int raw = cnt[q];
+        const int count = raw > cap ? cap : raw;
+        const int n_slots = (count + kCompactThreadsWide - 1) / kCompactThreadsWide;  // block-uniform
+#define KIRAG_TAIL_CASE(NS) \
+    compact_topm_body<NS, kCompactThreadsWide>(list, q, raw, count, cap, m, cnt, tau, overflow, nullptr, 0, sm)
+        if (n_slots <= 2) KIRAG_TAIL_CASE(2);
+        else if (n_slots <= 4) KIRAG_TAIL_CASE(4);
+        else if (n_slots <= 8) KIRAG_TAIL_CASE(8);
+        else if (n_slots <= 12) KIRAG_TAIL_CASE(12);
+        else if (n_slots <= 16) KIRAG_TAIL_CASE(16);
+        else if (n_slots <= 24) KIRAG_TAIL_CASE(24);
+        else KIRAG_TAIL_CASE(32);
+#undef KIRAG_TAIL_CASE
+        __threadfence();
     }
-    if (threadIdx.x == 0 && flags) {
-        int fail = 0;  // 0 ok, 1 certificate failed, 2 candidate buffer overflowed
-        const bool ovf = overflow && overflow[q];
-        if (check_cert && tau) {
-            const float t = tau[q];
-            if (t > -INFINITY) {
-                // something may have been dropped: need k valid results whose
-                // k-th score clears the dropped bound
-                if (k > P || item_key(items[k - 1]) == 0u) {
-                    fail = 1;
-                } else {
-                    const float kth = key_score(item_key(items[k - 1]));
-                    const float eps = eps_a * qnorm[q] + eps_b * qerr[q];
-                    if (!(kth - eps > t)) fail = 1;
-                }
-            }
+    cluster_barrier();
+    int keep = __ldcg(cnt + q);
+    if (keep > m) keep = m;
+    {
+        const int lane = threadIdx.x & 31;
+        const int gw = (int)crank * (kCompactThreadsWide / 32) + (threadIdx.x >> 5);
+        const int n_gw = (int)csize * (kCompactThreadsWide / 32);
+        const float* qrow = qmat + (int64_t)q * d;
+        for (int j = gw; j < keep; j += n_gw) {
+            const int32_t row = __ldcg(&list[j].id);
+            float result = __int_as_float(0x7fc00000);
+            if (row >= 0) result = warp_butterfly_sum(canonical_partial(master + (int64_t)row * d, qrow, d, lane, vec4 != 0));
+            if (lane == 0) __stcg(rescored + (int64_t)q * m + j, result);
         }
-        flags[q] = ovf ? 2 : fail;
+        __threadfence();
     }
+    cluster_barrier();
+    if (crank != 0) return;
+    const int P = next_pow2(keep > 0 ? keep : 1);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t it = 0ull;
+        if (i < keep) {
+            const int32_t id = __ldcg(&list[i].id);
+            if (id >= 0) it = pack_item(__ldcg(rescored + (int64_t)q * m + i), id);
+        }
+        items[i] = it;
+    }
+    __syncthreads();
+    final_body(items, P, q, q, k, D, I, id_offset, tau, qnorm, qerr, qcdot, eps_a, eps_b, 1, overflow, flags);
 }
 
 // ---- multi-GPU merge ---------------------------------------------------------
@@ -510,15 +625,15 @@ int launch_select_pairs(const Cand* in, int64_t in_stride, const int* cnt, int f
 }
 
 int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, int m, float* tau, int* overflow,
-                        cudaStream_t st) {
+                        float* tauk, int kth_k, cudaStream_t st) {
     KIRAG_CHECK(cap <= kWideCap && m <= cap, "compact_topm: cap=%d m=%d out of range", cap, m);
     if (nq <= 0) return 0;
     if (cap <= kSelectSeg) {
         KIRAG_CUDA_OK(launch_chained(compact_topm_kernel<kCompactThreads, 4>, dim3((unsigned)nq), dim3(kCompactThreads), 0,
-                                     st, buf, stride, cnt, cap, m, tau, overflow));
+                                     st, buf, stride, cnt, cap, m, tau, overflow, tauk, kth_k));
     } else {
         KIRAG_CUDA_OK(launch_chained(compact_topm_kernel<kCompactThreadsWide, 1>, dim3((unsigned)nq),
-                                     dim3(kCompactThreadsWide), 0, st, buf, stride, cnt, cap, m, tau, overflow));
+                                     dim3(kCompactThreadsWide), 0, st, buf, stride, cnt, cap, m, tau, overflow, tauk, kth_k));
     }
     KIRAG_LAUNCH_OK("compact_topm_kernel");
     return 0;
@@ -526,16 +641,47 @@ int launch_compact_topm(Cand* buf, int64_t stride, int* cnt, int cap, int nq, in
 
 int launch_final(const Cand* cand, int64_t cand_stride, const float* rescored, const int* cnt,
                  int fixed_count, int m_in, int nq, int k, float* D, int64_t* I, int64_t id_offset,
-                 const float* tau, const float* qnorm, const float* qerr, float eps_a, float eps_b, int check_cert,
-                 const int* overflow, int* flags, const int* qmap, cudaStream_t st) {
+                 const float* tau, const float* qnorm, const float* qerr, const float* qcdot, float eps_a, float eps_b,
+                 int check_cert, const int* overflow, int* flags, const int* qmap, cudaStream_t st) {
     KIRAG_CHECK(m_in <= kSelectSeg, "final: m_in=%d > %d", m_in, kSelectSeg);
     const int P = host_pow2(m_in);
     const size_t smem = (size_t)P * 8;
     if (ensure_smem(final_kernel, (size_t)kSelectSeg * 8)) return 1;
     KIRAG_CUDA_OK(launch_chained(final_kernel, dim3((unsigned)nq), dim3(sort_threads(P)), smem, st, cand, cand_stride,
-                                 rescored, cnt, fixed_count, m_in, k, D, I, id_offset, tau, qnorm, qerr, eps_a, eps_b, check_cert,
-                                 overflow, flags, qmap));
+                                 rescored, cnt, fixed_count, m_in, k, D, I, id_offset, tau, qnorm, qerr, qcdot, eps_a, eps_b,
+                                 check_cert, overflow, flags, qmap));
     KIRAG_LAUNCH_OK("final_kernel");
+    return 0;
+}
+
+int launch_tail_fused(Cand* buf, int64_t stride, int* cnt, int cap, int nq, int m, float* tau, int* overflow,
+                      const float* master, int d, const float* q, float* rescored, int k, float* D, int64_t* I,
+                      int64_t id_offset, const float* qnorm, const float* qerr, const float* qcdot, float eps_a, float eps_b,
+                      int* flags, int num_sms, cudaStream_t st) {
+    KIRAG_CHECK(cap <= kWideCap && m <= cap && m <= kTailMaxM, "tail_fused: cap=%d m=%d out of range", cap, m);
+    if (nq <= 0) return 0;
+    // cluster size: as many SMs per query as the GPU has to spare, at most 8 (the portable limit)
+    int C = 8;
+    while (C > 1 && (int64_t)nq * C > num_sms) C >>= 1;
+    const int vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(master) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nq * C));
+    cfg.blockDim = dim3(kCompactThreadsWide);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    KIRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, tail_fused_kernel, buf, stride, cnt, cap, m, tau, overflow, master, d, q, vec4,
+                                     rescored, k, D, I, id_offset, qnorm, qerr, qcdot, eps_a, eps_b, flags));
+    KIRAG_LAUNCH_OK("tail_fused_kernel");
     return 0;
 }
 

@@ -160,21 +160,22 @@ def test_level_schedule_covers_the_corpus_with_bounded_growth(n_rows, nq, k):
     grow the prefix by more than cap / (4 k') (expected survivors stay below a quarter of the buffer)."""
     n, hi, cap, kp = _schedule(n_rows, nq, k)
     assert n == len(hi) and n >= 1
-    assert kp == max(4 * k, 32)
+    assert kp == min(max(4 * k, 32), 2048)
     assert cap == (32768 if nq <= 128 else 8192)
     assert hi[-1] == n_rows
     assert all(a < b for a, b in zip(hi, hi[1:]))
     assert hi[0] == min(n_rows, cap // 2)
     gmax = max(2, min(32, cap // (4 * kp)))
     tiles = [-(-h // 128) for h in hi]
+    g1 = min(16 if cap == 32768 else 4, gmax)  # level 1: 4x with the normal buffer, 16x with the wide one
     for lvl, (a, b) in enumerate(zip(tiles, tiles[1:]), start=1):
-        limit = min(4, gmax) if lvl == 1 else gmax
+        limit = g1 if lvl == 1 else gmax
         assert b <= a * limit + 1, (lvl, a, b, limit)  # +1 tile: ceil of the geometric step
     # and it does not use more levels than a greedy walk with the same limits would
     t, greedy = tiles[0], 1
     n_tiles = tiles[-1]
     if t < n_tiles:
-        t, greedy = min(n_tiles, t * min(4, gmax)), 2
+        t, greedy = min(n_tiles, t * g1), 2
     while t < n_tiles:
         t, greedy = min(n_tiles, t * gmax), greedy + 1
     assert n <= greedy
@@ -185,7 +186,9 @@ def test_level_schedule_reference_points():
     assert _schedule(21_000_000, 4096, 100)[0] == 7
     assert _schedule(21_000_000, 32, 100)[0] == 4
     assert _schedule(2_625_000, 4096, 100)[0] == 6
-    assert _schedule(430_000, 64, 20)[0] == 3
+    assert _schedule(2_625_000, 32, 100)[0] == 3   # one 8-GPU shard, small batch: 16k / 262k / 2.6M rows
+    assert _schedule(5_200_000, 2, 10)[0] == 3
+    assert _schedule(430_000, 64, 20)[0] <= 3
     assert _schedule(1000, 4, 10)[1] == [1000]
 
 

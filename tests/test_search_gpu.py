@@ -206,7 +206,7 @@ def test_clustered_data_escalates_and_stays_exact(fa, monkeypatch):
     xq = (centers[:4] + 0.01 * unit_rows(rng, 4, 128)).astype(np.float32)
     ix = build(fa, xb)
     D, I, st = ix.search_ex(xq, 10, path=AUTO)
-    assert st["n_cert_fail"] >= 1 and st["n_rescan"] + st["n_exact"] == st["n_cert_fail"] + st["n_overflow"], st
+    assert st["n_cert_fail"] >= 1 and st["n_rescan"] + st["n_exact"] + st["n_retry"] == st["n_cert_fail"] + st["n_overflow"], st
     assert st["n_rescan"] >= 1, st
     assert_topk_parity(D, I, xb, xq, 10, what=f"clustered {st}")
     De, Ie, _ = ix.search_ex(xq, 10, path=EXACT)
@@ -384,7 +384,7 @@ def test_async_search_then_finish_equals_the_synchronous_call(fa):
     Da, Ia = ic.search_device_async(qc, 10)
     changed = ic.finish()
     st = ic.last_stats
-    assert changed >= 1 and st["n_cert_fail"] >= 1 and st["n_rescan"] + st["n_exact"] == changed, st
+    assert changed >= 1 and st["n_cert_fail"] >= 1 and st["n_rescan"] + st["n_exact"] + st["n_retry"] == changed, st
     assert torch.equal(Ia, Ie) and torch.equal(Da, De)
     # (c) an unfinished asynchronous search is completed by the next call on the handle
     Da, Ia = ic.search_device_async(qc, 10)
@@ -433,6 +433,73 @@ def test_k_above_512_stays_on_the_filter_path(fa):
     ix = build(fa, xb)
     for k in (600, 2048):
         D, I, st = ix.search_ex(xq, k, path=AUTO)
-        assert st["levels"] >= 2 and st["n_fast"] + st["n_rescan"] + st["n_exact"] == 3, st
+        assert st["levels"] >= 2 and st["n_fast"] + st["n_rescan"] + st["n_exact"] + st["n_retry"] == 3, st
         assert st["n_exact"] == 0, st
         assert_topk_parity(D, I, xb, xq, k, what=f"k={k} {st}")
+
+
+# ------------------------------------------------------- centred shadow / escalation ladder ---
+def e5_like_rows(rng, n, d, common=0.85):
+    """Rows with a large common component, like E5 embeddings (random-pair cosine ~ common^2 = 0.72)."""
+    mu = unit_rows(rng, 1, d)[0]
+    noise = rng.standard_normal((n, d)).astype(np.float32)
+    noise -= (noise @ mu)[:, None] * mu[None, :]
+    noise /= np.linalg.norm(noise, axis=1, keepdims=True)
+    x = common * mu[None, :] + np.sqrt(1.0 - common * common) * noise
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32), mu
+
+
+def test_e5_like_corpus_is_centred_and_certified(fa, monkeypatch):
+    """Embeddings with a large common component: the shadow stores bf16(x - c), the certificate bound scales with
+    ||x - c||, and (nearly) every query is certified on the first attempt; without centring the same corpus fails
+    its certificates and pays a second pass.  Results are the exact ones either way."""
+    rng = np.random.default_rng(31)
+    xb, mu = e5_like_rows(rng, 300_000, 512)
+    xq, _ = e5_like_rows(np.random.default_rng(32), 64, 512)
+    xq = (0.85 * mu[None, :] + (xq - (xq @ mu)[:, None] * mu[None, :])).astype(np.float32)
+    xq /= np.linalg.norm(xq, axis=1, keepdims=True)
+    assert float(np.mean(xb[:1000] @ xb[1000:2000].T)) > 0.65
+    ix = build(fa, xb)
+    D, I, st = ix.search_ex(xq, 100, path=AUTO)
+    assert st["n_fast"] >= 62, f"centred shadow should certify on the first attempt: {st}"
+    De, Ie, _ = ix.search_ex(xq, 100, path=EXACT)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De)
+    assert_topk_parity(D[:8], I[:8], xb, xq[:8], 100, what=f"e5-like {st}")
+    # the approximate scores the hook reports are still approximations of <q, x> (the centre is added back)
+    approx = ix.debug_scores(xq[:4])[:5000]
+    assert np.max(np.abs(approx - xb[:5000] @ xq[:4].T)) < 5e-3
+    # the same corpus without centring: certificates fail (that is what the centre is for), answers stay exact
+    monkeypatch.setenv("KIRAG_NO_CENTER", "1")
+    raw = build(fa, xb)
+    D2, I2, st2 = raw.search_ex(xq, 100, path=AUTO)
+    assert st2["n_cert_fail"] > st["n_cert_fail"] + 16, (st, st2)
+    assert np.array_equal(I2, Ie) and np.array_equal(D2, De)
+
+
+def test_centre_is_decided_late_for_small_first_adds(fa):
+    """The centring decision waits until 4096 rows are there; rows converted before it are re-converted."""
+    rng = np.random.default_rng(33)
+    xb, mu = e5_like_rows(rng, 20000, 128)
+    ix = fa.IndexFlatIP(128)
+    for a, b in ((0, 100), (100, 3000), (3000, 4096), (4096, 20000)):
+        ix.add(xb[a:b])
+    xq = xb[::1500] + 0.01 * rng.standard_normal((14, 128)).astype(np.float32)
+    D, I, st = ix.search_ex(xq.astype(np.float32), 10, path=AUTO)
+    De, Ie, _ = ix.search_ex(xq.astype(np.float32), 10, path=EXACT)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De), st
+    approx = ix.debug_scores(xq[:2].astype(np.float32))
+    assert np.max(np.abs(approx - xb @ xq[:2].T)) < 5e-3  # rows 0..4095 were re-converted with the centre
+
+
+def test_overflow_is_retried_with_the_gentle_schedule(fa, monkeypatch):
+    """A forced tiny candidate buffer overflows on the first attempt; the overflowed queries are re-answered by the
+    filter path with the gentle level schedule (n_retry), not by the exact fp32 scan."""
+    rng = np.random.default_rng(34)
+    xb, xq = unit_rows(rng, 400_000, 64), unit_rows(rng, 5, 64)
+    ix = build(fa, xb)
+    monkeypatch.setenv("KIRAG_LEVEL_GROWTH", "32")
+    monkeypatch.setenv("KIRAG_LEVEL1_GROWTH", "32")
+    monkeypatch.setenv("KIRAG_CAND_CAP", "1024")  # k' = 128: survivors of a 32x level ~ 4096 > 1024
+    D, I, st = ix.search_ex(xq, 32, path=AUTO)
+    assert st["n_overflow"] >= 1 and st["n_retry"] >= 1, st
+    assert_topk_parity(D, I, xb, xq, 32, what=f"retry {st}")
