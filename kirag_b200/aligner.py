@@ -29,22 +29,30 @@ class TripleScorer:
         self.n_embedded = 0  # triples actually sent through the encoder (for tests / accounting)
 
     def _ensure(self, texts: List[str]) -> torch.Tensor:
-        new = [t for t in dict.fromkeys(texts) if t not in self._row_of]
-        if new:
-            emb = self.embed_documents(new)
+        """Embeddings [len(texts), d] (CUDA) of `texts`, embedding only what the bank does not hold yet."""
+        wanted = list(dict.fromkeys(texts))
+        missing = [t for t in wanted if t not in self._row_of]
+        held = 0 if self._bank is None else self._bank.shape[0]
+        if missing and held + len(missing) > self.max_cached:
+            # the bank is full: start over with exactly what this call needs (everything is re-embedded once)
+            self._row_of.clear()
+            self._bank, held = None, 0
+            missing = wanted
+        if missing:
+            emb = self.embed_documents(missing)
             if not emb.is_cuda:
                 emb = emb.cuda()
             emb = emb.detach().float()
-            self.n_embedded += len(new)
-            base = 0 if self._bank is None else self._bank.shape[0]
-            if base + len(new) > self.max_cached:  # simple policy: start over
-                self._row_of.clear()
-                self._bank, base = None, 0
+            self.n_embedded += len(missing)
             self._bank = emb if self._bank is None else torch.cat([self._bank, emb], dim=0)
-            for i, t in enumerate(new):
-                self._row_of[t] = base + i
-        rows = torch.tensor([self._row_of[t] for t in texts], dtype=torch.int64, device=self._bank.device)
-        return self._bank.index_select(0, rows)
+            for i, t in enumerate(missing):
+                self._row_of[t] = held + i
+        rows = [self._row_of[t] for t in texts]
+        if rows == list(range(self._bank.shape[0])):
+            return self._bank  # the candidates ARE the bank, in order: no gather
+        if rows and rows == list(range(rows[0], rows[0] + len(rows))):
+            return self._bank[rows[0]:rows[0] + len(rows)]  # a contiguous run: a view
+        return self._bank.index_select(0, torch.tensor(rows, dtype=torch.int64, device=self._bank.device))
 
     def filter_candidate_triples(self, query_texts: List[str], triple_texts: List[str],
                                  num_candidate_triples: int) -> Tuple[List[List[int]], List[List[float]]]:

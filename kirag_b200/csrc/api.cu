@@ -174,6 +174,7 @@ struct FastParams {
     int growth_override;  // KIRAG_LEVEL_GROWTH (0: automatic)
     int cap_override;     // KIRAG_CAND_CAP (0: automatic)
     int first_growth_override;  // KIRAG_LEVEL1_GROWTH (0: automatic)
+    int few_queries;            // the call has at most kFewQueries queries (set per call)
 };
 
 struct SearchCounters {
@@ -391,6 +392,7 @@ static int exact_search(kirag_index* h, const float* qsub, int64_t nsub, int k, 
 // there (HBM-bound), launches are what costs, and a 4x larger g_max removes two to three levels.
 constexpr int64_t kWideCapMaxQueries = 128;
 constexpr int64_t kQChunk = 16384;  // queries per pass of the search workspaces
+constexpr int64_t kFewQueries = 8;
 constexpr int kMaxGrowth = 32;
 
 
@@ -428,9 +430,11 @@ static std::vector<int64_t> level_bounds(int64_t n_tiles, int cap, const FastPar
     if (gmax > kMaxGrowth) gmax = kMaxGrowth;
     if (fp.growth_override > 0) gmax = fp.growth_override;
     if (gmax < 2) gmax = 2;
-    // growth of level 1: 4 for the normal buffer; 16 for the wide buffer of small batches, where a level costs a
-    // fixed ~40 us of launch / ramp / compaction latency and an overflow is re-answered with the gentle schedule
-    int g1 = (cap >= kWideCap) ? 16 : 4;
+    // growth of level 1: 4; 16 for calls of at most kFewQueries queries (KiRAG's own shape: 1-2 queries per
+    // retrieval), where one level less is worth ~35 us per call on a 2.6M-row shard (0.92 -> 0.88 ms).  With 32 or
+    // more queries the 4x more survivors of a 16x level cost more than the level saves (measured: 0.92 -> 0.95 ms
+    // at 32 queries, gpurun_out/r2f_knobs.log).  An overflow is re-answered with the gentle schedule.
+    int g1 = (cap >= kWideCap && fp.few_queries) ? 16 : 4;
     if (fp.first_growth_override > 0) g1 = fp.first_growth_override;
     if (g1 > gmax) g1 = gmax;
     t = t * g1;
@@ -528,7 +532,9 @@ static int fast_search(kirag_index* h, const float* qd, int64_t nq, int k, float
 
     const int64_t n_tiles = (n + kTileRows - 1) / kTileRows;
     const int64_t mult = pick_tile_mult(n_tiles);
-    const std::vector<int64_t> bounds = level_bounds(n_tiles, cap, fp);
+    FastParams fpl = fp;
+    fpl.few_queries = nq <= kFewQueries ? 1 : 0;
+    const std::vector<int64_t> bounds = level_bounds(n_tiles, cap, fpl);
     int64_t lo = 0;
     int levels = 0;
     for (const int64_t hi : bounds) {
@@ -1198,6 +1204,7 @@ int kirag_debug_level_schedule(int64_t n_rows, int64_t nq, int k, int d, int64_t
     fp.first_growth_override = env_int("KIRAG_LEVEL1_GROWTH", 0);
     if (fp.cap_override > 0 && fp.cap_override < 4 * kp) return -1;
     const int cap = pick_cap(fp, nq);
+    fp.few_queries = nq <= kFewQueries ? 1 : 0;
     const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
     const std::vector<int64_t> b = level_bounds(n_tiles, cap, fp);
     if ((int)b.size() > max_levels) {

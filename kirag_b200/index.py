@@ -1,89 +1,125 @@
-"""`Indexer` with the reference's interface, on the B200 library.
+"""`Indexer` / `ShardedIndexer`: the reference's indexer interface on the B200 library.
 
-Mirror of /root/reference/retriever/index.py:17-83 (same method names,
-argument meaning, return types and error behaviour) for callers that import
-an indexer class directly instead of going through `kirag_b200.as_faiss`.
-Differences are confined to host-side glue that the reference does in Python
-loops: ids are mapped with one vectorised numpy take instead of an n*k
-`str()` list comprehension per element (index.py:49), and the id map grows by
-chunks instead of `np.concatenate` per call (index.py:81-83).
+The reference's own `retriever/index.py` runs unmodified on `kirag_b200.as_faiss` (tests/test_reference_*_gpu.py);
+this module is for callers that want an indexer object WITHOUT the reference on their path.  `Indexer` offers the
+public surface of /root/reference/retriever/index.py:17-83 — `index_data`, `search_knn`, `serialize`,
+`deserialize_from`, the attributes `index` and `index_id_to_db_id`, the file names `index.faiss` /
+`index_meta.faiss` and the return shape `[(ids: list[str], scores: float32[k]), ...]` — and is written around what
+differs from the reference's glue:
+
+  * the row -> passage-id table is an amortised-growth int64 array (the reference re-concatenates the whole table
+    on every `index_data`, index.py:81-83: O(total) per call);
+  * row numbers are turned into passage-id strings with ONE vectorised take + `astype(str)` per faiss call (the
+    reference runs a Python `str()` per result, index.py:49: 1.6M calls at 16384 queries x 100);
+  * only the exact inner-product index exists here (the only one any KiRAG caller constructs: retrieve.py:112,
+    faiss_index_corpus.py:29); asking for "l2" or product quantisation fails at construction.
 """
 from __future__ import annotations
 
 import logging
 import os
 import pickle
-from typing import List, Tuple
+from typing import Iterable, List, Sequence, Tuple
 
 import numpy as np
 
 from . import faiss_api
 
-logger = logging.getLogger()
+logger = logging.getLogger(__name__)
 
-FAISSINDEX_DICT = {
-    "inner_product": faiss_api.IndexFlatIP,
-    "l2": faiss_api.IndexFlatL2,
-}
+INDEX_FILE = "index.faiss"      # index.py:57,68
+META_FILE = "index_meta.faiss"  # index.py:58,69
+# metric name -> index class; tests substitute a CPU test double here
+INDEX_TYPES = {"inner_product": faiss_api.IndexFlatIP}
 
 
-class Indexer(object):
+class _PassageIds:
+    """Append-only int64 table: index row -> passage id, with amortised growth."""
+
+    def __init__(self, initial: Sequence[int] = ()):
+        self._buf = np.array(initial, dtype=np.int64).reshape(-1)
+        self._n = self._buf.shape[0]
+
+    def extend(self, ids: Iterable) -> None:
+        new = np.asarray(list(ids) if not isinstance(ids, np.ndarray) else ids)
+        new = new.astype(np.int64).reshape(-1)  # "123" -> 123, like np.array(db_ids, dtype=np.int64) in the reference
+        need = self._n + new.shape[0]
+        if need > self._buf.shape[0]:
+            grown = np.empty(max(need, 2 * self._buf.shape[0], 1024), dtype=np.int64)
+            grown[:self._n] = self._buf[:self._n]
+            self._buf = grown
+        self._buf[self._n:need] = new
+        self._n = need
+
+    def view(self) -> np.ndarray:
+        return self._buf[:self._n]
+
+    def __len__(self) -> int:
+        return self._n
+
+
+class Indexer:
 
     def __init__(self, vector_sz, metric="inner_product", n_subquantizers=0, n_bits=8, device=None):
         if n_subquantizers > 0:
-            self.index = faiss_api.IndexPQ(vector_sz, n_subquantizers, n_bits, faiss_api.METRIC_INNER_PRODUCT)
-        else:
-            self.index = FAISSINDEX_DICT[metric](vector_sz) if device is None else \
-                FAISSINDEX_DICT[metric](vector_sz, device=device)
-        self.index_id_to_db_id = np.empty((0), dtype=np.int64)
+            raise NotImplementedError("product quantisation is not part of this library (no KiRAG caller uses it)")
+        if metric not in INDEX_TYPES:
+            raise NotImplementedError(f"metric {metric!r}: only 'inner_product' is implemented "
+                                      "(the only metric KiRAG constructs)")
+        make = INDEX_TYPES[metric]
+        self.index = make(int(vector_sz)) if device is None else make(int(vector_sz), device=device)
+        self._ids = _PassageIds()
 
-    def index_data(self, ids, embeddings):
-        self._update_id_mapping(ids)
-        embeddings = embeddings.astype('float32')
-        if not self.index.is_trained:
-            self.index.train(embeddings)
-        self.index.add(embeddings)
-        logger.info(f'Total data indexed {len(self.index_id_to_db_id)}')
+    # the reference exposes the table as a plain attribute; keep it readable and assignable
+    @property
+    def index_id_to_db_id(self) -> np.ndarray:
+        return self._ids.view()
 
-    def search_knn(self, query_vectors: np.array, top_docs: int, index_batch_size=1024,
-                   verbose: bool = True) -> List[Tuple[List[object], List[float]]]:
-        query_vectors = query_vectors.astype('float32')
-        result = []
-        nbatch = (len(query_vectors) - 1) // index_batch_size + 1
-        for k in range(nbatch):
-            start_idx = k * index_batch_size
-            end_idx = min((k + 1) * index_batch_size, len(query_vectors))
-            q = query_vectors[start_idx:end_idx]
-            scores, indexes = self.index.search(q, top_docs)
-            # convert to external ids; -1 padding indexes the LAST id exactly like
-            # the reference's index_id_to_db_id[-1] does (index.py:49)
-            db_ids = self.index_id_to_db_id[indexes].astype(str).tolist() if len(self.index_id_to_db_id) else \
-                [[str(i) for i in row] for row in indexes]
-            result.extend([(db_ids[i], scores[i]) for i in range(len(db_ids))])
-        return result
+    @index_id_to_db_id.setter
+    def index_id_to_db_id(self, table) -> None:
+        self._ids = _PassageIds(np.asarray(table, dtype=np.int64))
 
-    def serialize(self, dir_path):
-        index_file = os.path.join(dir_path, "index.faiss")
-        meta_file = os.path.join(dir_path, "index_meta.faiss")
-        logger.info(f'Serializing index to {index_file}, meta data to {meta_file}')
+    def index_data(self, ids, embeddings) -> None:
+        """Append rows `embeddings` [n, d] (any float dtype) whose passage ids are `ids` (int-parsable)."""
+        rows = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if len(ids) != rows.shape[0]:
+            raise AssertionError(f"{len(ids)} ids for {rows.shape[0]} embeddings")
+        self._ids.extend(ids)
+        self.index.add(rows)
+        logger.info("Total data indexed %d", len(self._ids))
+
+    def _rows_to_ids(self, rows: np.ndarray) -> List[List[str]]:
+        table = self._ids.view()
+        if table.shape[0] == 0:
+            return rows.astype(str).tolist()
+        # numpy's negative indexing maps FAISS's -1 padding to the LAST id, which is what the reference's
+        # `self.index_id_to_db_id[i]` does with it (index.py:49)
+        return table[rows].astype(str).tolist()
+
+    def search_knn(self, query_vectors, top_docs: int, index_batch_size: int = 1024,
+                   verbose: bool = True) -> List[Tuple[List[str], np.ndarray]]:
+        queries = np.ascontiguousarray(query_vectors, dtype=np.float32)
+        out: List[Tuple[List[str], np.ndarray]] = []
+        for lo in range(0, queries.shape[0], int(index_batch_size)):
+            scores, rows = self.index.search(queries[lo:lo + int(index_batch_size)], top_docs)
+            out.extend(zip(self._rows_to_ids(rows), scores))
+        return out
+
+    def serialize(self, dir_path) -> None:
+        index_file, meta_file = os.path.join(dir_path, INDEX_FILE), os.path.join(dir_path, META_FILE)
+        logger.info("Serializing index to %s, meta data to %s", index_file, meta_file)
         faiss_api.write_index(self.index, index_file)
-        with open(meta_file, mode='wb') as f:
-            pickle.dump(self.index_id_to_db_id, f)
+        with open(meta_file, "wb") as f:
+            pickle.dump(np.array(self._ids.view()), f)  # a plain int64 ndarray, as the reference pickles
 
-    def deserialize_from(self, dir_path):
-        index_file = os.path.join(dir_path, "index.faiss")
-        meta_file = os.path.join(dir_path, "index_meta.faiss")
-        logger.info(f'Loading index from {index_file}, meta data from {meta_file}')
+    def deserialize_from(self, dir_path) -> None:
+        index_file, meta_file = os.path.join(dir_path, INDEX_FILE), os.path.join(dir_path, META_FILE)
+        logger.info("Loading index from %s, meta data from %s", index_file, meta_file)
         self.index = faiss_api.read_index(index_file, faiss_api.IO_FLAG_MMAP)
-        logger.info('Loaded index of type %s and size %d', type(self.index), self.index.ntotal)
-        with open(meta_file, "rb") as reader:
-            self.index_id_to_db_id = pickle.load(reader)
-        assert len(
-            self.index_id_to_db_id) == self.index.ntotal, 'Deserialized index_id_to_db_id should match faiss index size'
-
-    def _update_id_mapping(self, db_ids: List):
-        new_ids = np.array(db_ids, dtype=np.int64)
-        self.index_id_to_db_id = np.concatenate((self.index_id_to_db_id, new_ids), axis=0)
+        with open(meta_file, "rb") as f:
+            self.index_id_to_db_id = pickle.load(f)
+        if len(self._ids) != self.index.ntotal:
+            raise AssertionError(f"{meta_file} holds {len(self._ids)} passage ids, {index_file} {self.index.ntotal} rows")
 
 
 class ShardedIndexer(object):

@@ -47,20 +47,25 @@ class DeviceDenseRetriever(torch.nn.Module):
         self.batch_size = batch_size
         self.kwargs = kwargs
 
-    # -- same helpers as the reference ------------------------------------------------------
+    # -- result materialisation ---------------------------------------------------------------
+    def _hit(self, docid, score=None) -> dict:
+        """One result entry: a private copy of the corpus document (callers mutate results) with its score, or the
+        bare {"id", "score"} pair when there is no corpus (retrievers.py:265-272)."""
+        if self.corpus is None:
+            return {"id": docid, "score": score}
+        doc = deepcopy(self.corpus.get_document(docid))
+        if score is not None:
+            doc["score"] = float(score)
+        return doc
+
     def get_documents(self, docid_list: Union[List[str], Dict[str, float]]) -> List[dict]:
-        documents = []
+        """Documents for a list of ids (in order), or for an {id: score} dict (best score first, with "score")."""
+        if isinstance(docid_list, dict):
+            ranked = sorted(docid_list.items(), key=lambda item: item[1], reverse=True)
+            return [self._hit(docid, score) for docid, score in ranked]
         if isinstance(docid_list, list):
-            for docid in docid_list:
-                documents.append(deepcopy(self.corpus.get_document(docid)))
-        elif isinstance(docid_list, dict):
-            for docid, score in sorted(docid_list.items(), key=lambda x: x[1], reverse=True):
-                document = deepcopy(self.corpus.get_document(docid))
-                document["score"] = float(score)
-                documents.append(document)
-        else:
-            raise ValueError(f"{type(docid_list)} is not a supported type for \"docid_list\"!")
-        return documents
+            return [self._hit(docid) for docid in docid_list]
+        raise ValueError(f"{type(docid_list)} is not a supported type for \"docid_list\"!")
 
     @torch.no_grad()
     def calculate_query_embeddings(self, queries: List[str], max_length: int = None, verbose: bool = False,
@@ -93,19 +98,8 @@ class DeviceDenseRetriever(torch.nn.Module):
         return ids, D
 
     def parse_indexer_output(self, indexer_output) -> List[List[dict]]:
-        """Same contract as retrievers.py:234-248: [(ids, scores), ...] -> [[document dict + "score", ...], ...]."""
-        retrieval_results = []
-        for topk_str_indices, topk_score_array in indexer_output:
-            one = []
-            for docid, score in zip(topk_str_indices, topk_score_array):
-                if self.corpus is not None:
-                    document = deepcopy(self.corpus.get_document(docid))
-                    document["score"] = float(score)
-                else:
-                    document = {"id": docid, "score": score}
-                one.append(document)
-            retrieval_results.append(one)
-        return retrieval_results
+        """[(ids, scores), ...] as returned by `search_knn` -> one list of result entries per query."""
+        return [[self._hit(docid, score) for docid, score in zip(ids, scores)] for ids, scores in indexer_output]
 
     def batch_retrieve(self, queries: List[str], topk: int, verbose: bool = False, **kwargs) -> List[dict]:
         emb = self.calculate_query_embeddings(queries=queries, verbose=verbose, **kwargs)

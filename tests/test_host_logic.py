@@ -61,7 +61,7 @@ class _OracleBackedIndex(oracle.OracleIndexFlatIP):
 
 
 def test_indexer_mirror_glue_on_a_test_double(tmp_path, monkeypatch):
-    monkeypatch.setitem(kindex.FAISSINDEX_DICT, "inner_product", _OracleBackedIndex)
+    monkeypatch.setitem(kindex.INDEX_TYPES, "inner_product", _OracleBackedIndex)
     monkeypatch.setattr(faiss_api, "write_index", oracle._write_index)
     monkeypatch.setattr(faiss_api, "read_index", oracle._read_index)
     rng = np.random.default_rng(1)
@@ -167,7 +167,7 @@ def test_level_schedule_covers_the_corpus_with_bounded_growth(n_rows, nq, k):
     assert hi[0] == min(n_rows, cap // 2)
     gmax = max(2, min(32, cap // (4 * kp)))
     tiles = [-(-h // 128) for h in hi]
-    g1 = min(16 if cap == 32768 else 4, gmax)  # level 1: 4x with the normal buffer, 16x with the wide one
+    g1 = min(16 if (cap == 32768 and nq <= 8) else 4, gmax)  # level 1: 4x; 16x for calls of at most 8 queries
     for lvl, (a, b) in enumerate(zip(tiles, tiles[1:]), start=1):
         limit = g1 if lvl == 1 else gmax
         assert b <= a * limit + 1, (lvl, a, b, limit)  # +1 tile: ceil of the geometric step
@@ -186,7 +186,8 @@ def test_level_schedule_reference_points():
     assert _schedule(21_000_000, 4096, 100)[0] == 7
     assert _schedule(21_000_000, 32, 100)[0] == 4
     assert _schedule(2_625_000, 4096, 100)[0] == 6
-    assert _schedule(2_625_000, 32, 100)[0] == 3   # one 8-GPU shard, small batch: 16k / 262k / 2.6M rows
+    assert _schedule(2_625_000, 32, 100)[0] == 4
+    assert _schedule(2_625_000, 2, 100)[0] == 3    # one 8-GPU shard, KiRAG's call shape: 16k / 262k / 2.6M rows
     assert _schedule(5_200_000, 2, 10)[0] == 3
     assert _schedule(430_000, 64, 20)[0] <= 3
     assert _schedule(1000, 4, 10)[1] == [1000]
@@ -197,3 +198,49 @@ def test_level_schedule_ineligible_shapes():
     # k > 512: the over-fetch is capped at k' = 2048, the filter path still takes it (k <= 2048)
     n_levels, bounds, cap, kprime = _schedule(1_000_000, 4, 1024)
     assert n_levels > 0 and kprime == 2048 and cap >= 4 * kprime and bounds[-1] == 1_000_000
+
+
+def test_indexer_rejects_what_it_does_not_implement():
+    with pytest.raises(NotImplementedError):
+        kindex.Indexer(8, metric="l2")
+    with pytest.raises(NotImplementedError):
+        kindex.Indexer(8, n_subquantizers=4)
+
+
+def test_passage_id_table_grows_amortised_and_accepts_strings():
+    t = kindex._PassageIds()
+    t.extend(["5", "6"])
+    t.extend(np.arange(7, 3000))
+    t.extend([])
+    assert len(t) == 2995 and t.view()[:3].tolist() == [5, 6, 7] and t.view().dtype == np.int64
+
+
+def test_triple_scorer_cache_reset_keeps_the_current_call_consistent():
+    """when the bank overflows max_cached it is rebuilt from EVERYTHING the current call needs (texts that
+    were cached before the reset included), not only from the texts that were new."""
+    import torch
+
+    from kirag_b200 import aligner
+
+    calls = []
+
+    def embed(texts):
+        calls.append(list(texts))
+        return torch.tensor([[float(x), 1.0] for x in texts])
+
+    sc = aligner.TripleScorer(embed_queries=embed, embed_documents=embed, max_cached=5)
+    # run the bookkeeping on CPU tensors: _ensure only moves tensors that are not CUDA, so patch .cuda() away
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        a = sc._ensure(["1", "2", "3"])
+        assert a[:, 0].tolist() == [1.0, 2.0, 3.0] and sc.n_embedded == 3
+        b = sc._ensure(["3", "2"])  # cached, permuted: a gather
+        assert b[:, 0].tolist() == [3.0, 2.0] and sc.n_embedded == 3
+        c = sc._ensure(["2", "3", "4", "5", "6", "7"])  # 3 held + 4 new > 5: the bank starts over with all six
+        assert c[:, 0].tolist() == [2.0, 3.0, 4.0, 5.0, 6.0, 7.0]
+        assert calls[-1] == ["2", "3", "4", "5", "6", "7"] and len(sc._row_of) == 6
+        d = sc._ensure(["4", "5"])  # contiguous run of the bank: a view, nothing embedded
+        assert d[:, 0].tolist() == [4.0, 5.0] and sc.n_embedded == 9
+    finally:
+        torch.Tensor.cuda = orig_cuda

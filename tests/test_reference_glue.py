@@ -57,7 +57,7 @@ def test_reference_indexer_runs_unmodified_on_the_oracle(ref_index_module, tmp_p
 def test_mirror_and_reference_indexer_agree(ref_index_module, monkeypatch):
     from kirag_b200 import index as kindex
 
-    monkeypatch.setitem(kindex.FAISSINDEX_DICT, "inner_product", oracle.OracleIndexFlatIP)
+    monkeypatch.setitem(kindex.INDEX_TYPES, "inner_product", oracle.OracleIndexFlatIP)
     rng = np.random.default_rng(3)
     xb, xq = int_corpus(rng, 120, 16), int_corpus(rng, 2500, 16)  # > 2 batches of 1024
     ids = list(range(500, 620))
