@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "../../include/kirag_b200.h"
 
+#include <cuda.h>  // driver-API TYPES only: the entry points are fetched with cudaGetDriverEntryPoint (no -lcuda)
+
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -169,6 +171,107 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
 
 using namespace kirag;
 
+// ------------------------------------------------------------- growable device storage ---
+// The corpus (fp32 master + bf16 shadow: 129 GB at 21M x 1024) must be able to GROW — the reference's build path
+// calls index.add() once per 1M-row file with no reserve hook (faiss_index_corpus.py:42-46) — without ever holding
+// two copies: cudaMalloc(new) + copy + cudaFree(old) needs old + new resident at once, which does not fit a 180 GB
+// GPU beyond ~40 % fill.  So each buffer is a reserved VIRTUAL address range into which physical
+// chunks are mapped as the index grows (cuMemAddressReserve / cuMemCreate / cuMemMap): growing maps one more
+// chunk at the end, nothing is copied, the base address never changes.
+struct VmmApi {
+    bool ok = false;
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+};
+static const VmmApi& vmm_api() {
+    static const VmmApi api = [] {
+        VmmApi a;
+        const char* off = getenv("KIRAG_NO_VMM");
+        if (off && *off && atoi(off) != 0) return a;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult qr;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &qr) == cudaSuccess &&
+                   qr == cudaDriverEntryPointSuccess && *fn != nullptr;
+        };
+        a.ok = get("cuMemAddressReserve", (void**)&a.AddressReserve) && get("cuMemAddressFree", (void**)&a.AddressFree) &&
+               get("cuMemCreate", (void**)&a.Create) && get("cuMemRelease", (void**)&a.Release) &&
+               get("cuMemMap", (void**)&a.Map) && get("cuMemUnmap", (void**)&a.Unmap) &&
+               get("cuMemSetAccess", (void**)&a.SetAccess) &&
+               get("cuMemGetAllocationGranularity", (void**)&a.GetGranularity);
+        cudaGetLastError();
+        return a;
+    }();
+    return api;
+}
+
+struct VmBuffer {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0, gran = 0;
+    int device = 0;
+    struct Chunk { CUmemGenericAllocationHandle h; size_t off, size; };
+    std::vector<Chunk> chunks;
+
+    bool active() const { return base != 0; }
+    void* ptr() const { return reinterpret_cast<void*>(base); }
+
+    CUmemAllocationProp prop() const {
+        CUmemAllocationProp p = {};
+        p.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        p.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        p.location.id = device;
+        return p;
+    }
+    // reserve `bytes` of address space (no physical memory yet)
+    int reserve(int dev, size_t bytes) {
+        const VmmApi& a = vmm_api();
+        if (!a.ok) return 1;
+        device = dev;
+        const CUmemAllocationProp p = prop();
+        if (a.GetGranularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return 1;
+        reserved = (bytes + gran - 1) / gran * gran;
+        if (a.AddressReserve(&base, reserved, 0, 0, 0) != CUDA_SUCCESS) { base = 0; reserved = 0; return 1; }
+        return 0;
+    }
+    // make [0, bytes) usable; 0 ok, 1 out of (physical or reserved) memory — nothing is changed then
+    int ensure(size_t bytes) {
+        if (bytes <= mapped) return 0;
+        const VmmApi& a = vmm_api();
+        const size_t want = (bytes + gran - 1) / gran * gran;
+        if (want > reserved) return 1;
+        Chunk c;
+        c.off = mapped;
+        c.size = want - mapped;
+        const CUmemAllocationProp p = prop();
+        if (a.Create(&c.h, c.size, &p, 0) != CUDA_SUCCESS) return 1;
+        if (a.Map(base + c.off, c.size, 0, c.h, 0) != CUDA_SUCCESS) { a.Release(c.h); return 1; }
+        CUmemAccessDesc acc = {};
+        acc.location = p.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (a.SetAccess(base + c.off, c.size, &acc, 1) != CUDA_SUCCESS) {
+            a.Unmap(base + c.off, c.size);
+            a.Release(c.h);
+            return 1;
+        }
+        chunks.push_back(c);
+        mapped = want;
+        return 0;
+    }
+    void release() {
+        const VmmApi& a = vmm_api();
+        for (auto& c : chunks) { a.Unmap(base + c.off, c.size); a.Release(c.h); }
+        chunks.clear();
+        if (base) a.AddressFree(base, reserved);
+        base = 0;
+        reserved = mapped = 0;
+    }
+};
+
 struct FastParams {
     int kprime;
     int growth_override;  // KIRAG_LEVEL_GROWTH (0: automatic)
@@ -207,6 +310,8 @@ struct kirag_index {
     int64_t capacity = 0;       // rows
     float* master = nullptr;    // [capacity, d] fp32
     uint8_t* shadow = nullptr;  // bf16 tiles, capacity rounded up to 128 rows (null if d % 64)
+    VmBuffer vm_master, vm_shadow;  // where master / shadow live when virtual-memory growth is available
+    bool use_vmm = false;
     unsigned* maxnorm2_bits = nullptr;  // device: [0] max ||y||^2, [1] max ||y - bf16(y)||^2, [2] max ||x||^2 (float bits)
     float maxnorm = 0.f;                // max_j ||y_j||, y = x - center (= x without a centre): what the shadow holds
     float maxerr = 0.f;                 // max_j ||y_j - bf16(y_j)||
@@ -282,58 +387,74 @@ static int decide_center(kirag_index* h, int64_t rows_available, cudaStream_t st
 
 static int index_grow(kirag_index* h, int64_t need_rows, cudaStream_t st) {
     if (need_rows <= h->capacity) return 0;
-    int64_t cap = h->capacity + h->capacity / 2;
-    if (cap < need_rows) cap = need_rows;
-    cap = round_up(cap, kTileRows);
-    float* nm = nullptr;
-    uint8_t* ns = nullptr;
-    const size_t mbytes = (size_t)cap * h->d * sizeof(float);
-    cudaError_t e = cudaMalloc((void**)&nm, mbytes);
-    if (e != cudaSuccess) {
-        set_error("cudaMalloc of the fp32 master (%zu bytes for %lld rows) failed: %s", mbytes,
-                  (long long)cap, cudaGetErrorString(e));
-        return 1;
-    }
     const bool want_shadow = scan_tc_supported(h->d) != 0;
-    if (want_shadow) {
-        const size_t sbytes = (size_t)cap * h->d * 2;
-        e = cudaMalloc((void**)&ns, sbytes);
-        if (e != cudaSuccess) {
-            cudaFree(nm);
-            set_error("cudaMalloc of the bf16 shadow (%zu bytes) failed: %s", sbytes, cudaGetErrorString(e));
-            return 1;
+    const size_t row_m = (size_t)h->d * sizeof(float), row_s = (size_t)h->d * 2;
+    if (h->capacity == 0 && !h->master && vmm_api().ok) {
+        // address space for the largest index this GPU could ever hold (the whole device memory as fp32 rows)
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) {
+            const size_t max_rows = (size_t)round_up((int64_t)(total_b / row_m) + kTileRows, kTileRows);
+            if (h->vm_master.reserve(h->device, max_rows * row_m) == 0 &&
+                (!want_shadow || h->vm_shadow.reserve(h->device, max_rows * row_s) == 0)) {
+                h->use_vmm = true;
+                h->master = static_cast<float*>(h->vm_master.ptr());
+                h->shadow = want_shadow ? static_cast<uint8_t*>(h->vm_shadow.ptr()) : nullptr;
+            } else {
+                h->vm_master.release();
+                h->vm_shadow.release();
+            }
         }
-        // rows beyond ntotal in the last tile are masked by the scan, but keep them finite
-        if (cudaMemsetAsync(ns, 0, sbytes, st) != cudaSuccess) {
-            cudaFree(nm); cudaFree(ns);
-            set_error("cudaMemsetAsync(shadow) failed");
-            return 1;
-        }
+        cudaGetLastError();
     }
-    if (h->ntotal > 0) {
-        cudaError_t e1 = cudaMemcpyAsync(nm, h->master, (size_t)h->ntotal * h->d * sizeof(float),
-                                         cudaMemcpyDeviceToDevice, st);
-        cudaError_t e2 = cudaSuccess;
-        if (want_shadow && h->shadow) {
-            // copy whole tiles; the partial last tile is copied too (overwrites the zeros)
-            e2 = cudaMemcpyAsync(ns, h->shadow, (size_t)round_up(h->ntotal, kTileRows) * h->d * 2,
-                                 cudaMemcpyDeviceToDevice, st);
+    // grow by a quarter beyond what is needed (amortises the mapping calls of many small adds); when that does
+    // not fit any more, by exactly what is needed
+    int64_t cap = round_up(need_rows > h->capacity + h->capacity / 4 ? need_rows : h->capacity + h->capacity / 4, kTileRows);
+    const int64_t exact = round_up(need_rows, kTileRows);
+    if (h->use_vmm) {
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const int64_t c = attempt == 0 ? cap : exact;
+            // nothing has to be undone on failure: a mapped-but-unused tail of the master is just capacity
+            if (h->vm_master.ensure((size_t)c * row_m) == 0 && (!want_shadow || h->vm_shadow.ensure((size_t)c * row_s) == 0)) {
+                h->capacity = c;
+                return 0;
+            }
+            if (cap == exact) break;
         }
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            cudaFree(nm); if (ns) cudaFree(ns);
-            set_error("device copy while growing the index failed");
-            return 1;
-        }
-    }
-    if (cudaStreamSynchronize(st) != cudaSuccess) {
-        cudaFree(nm); if (ns) cudaFree(ns);
-        set_error("stream sync while growing the index failed: %s", cudaGetErrorString(cudaGetLastError()));
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        set_error("index storage for %lld rows x %d (fp32 master%s) does not fit: %zu MiB free of %zu MiB",
+                  (long long)exact, h->d, want_shadow ? " + bf16 shadow" : "", free_b >> 20, total_b >> 20);
+        cudaGetLastError();
         return 1;
     }
-    if (h->master) cudaFree(h->master);
-    if (h->shadow) cudaFree(h->shadow);
-    h->master = nm;
-    h->shadow = ns;
+    // no virtual-memory API (KIRAG_NO_VMM=1 / old driver): cudaMalloc + copy, one buffer after the other so that
+    // at most ONE buffer exists twice at any time
+    auto regrow = [&](void** buf, size_t row_bytes, size_t live_rows, const char* what) -> int {
+        void* nb = nullptr;
+        int64_t c = cap;
+        cudaError_t e = cudaMalloc(&nb, (size_t)c * row_bytes);
+        if (e != cudaSuccess && cap != exact) { cudaGetLastError(); c = exact; e = cudaMalloc(&nb, (size_t)c * row_bytes); }
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc of the %s (%zu bytes for %lld rows) failed: %s", what, (size_t)c * row_bytes, (long long)c,
+                      cudaGetErrorString(e));
+            cudaGetLastError();
+            return 1;
+        }
+        if (*buf && live_rows > 0) {
+            if (cudaMemcpyAsync(nb, *buf, live_rows * row_bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) {
+                cudaFree(nb);
+                set_error("device copy while growing the %s failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        }
+        if (*buf) cudaFree(*buf);
+        *buf = nb;
+        cap = c;  // the second buffer must not be larger than the first
+        return 0;
+    };
+    if (regrow((void**)&h->master, row_m, (size_t)h->ntotal, "fp32 master")) return 1;
+    if (want_shadow && regrow((void**)&h->shadow, row_s, (size_t)round_up(h->ntotal, kTileRows), "bf16 shadow")) return 1;
     h->capacity = cap;
     return 0;
 }
@@ -880,6 +1001,42 @@ static int search_impl(kirag_index* h, const float* q, int64_t nq, int k, float*
     return 0;
 }
 
+// Rows [r0, r0 + n) of the master are in place: (re)decide the centre if it is time, convert them to the shadow
+// and refresh the norm maxima.  One pass, one synchronisation.
+static int finalize_rows(kirag_index* h, int64_t r0, int64_t n, cudaStream_t st) {
+    if (h->shadow && !h->center_decided && r0 + n >= kCenterMinRows) {
+        if (decide_center(h, r0 + n, st)) return 1;
+        h->center_decided = true;
+        if (h->center && r0 > 0) {
+            KIRAG_CUDA_OK(cudaMemsetAsync(h->maxnorm2_bits, 0, 8, st));
+            if (launch_convert_rows(h->master, r0, h->d, 0, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, nullptr, h->center,
+                                    nullptr, st)) return 1;
+        }
+    }
+    if (launch_convert_rows(h->master + r0 * (int64_t)h->d, n, h->d, r0, h->shadow, kTileRows, h->maxnorm2_bits, nullptr,
+                            nullptr, h->center, nullptr, st)) return 1;
+    if (h->shadow && ((r0 + n) % kTileRows) != 0) {
+        // rows of the last tile beyond ntotal: masked by the scan, but newly mapped memory is not zeroed — keep them
+        // finite.  In the block layout rows rr..127 of a tile are the tail of each of its d/64 16-KB blocks.
+        const int64_t end = r0 + n;
+        const int64_t tile = end / kTileRows;
+        const int rr = (int)(end - tile * kTileRows);
+        uint8_t* tile_base = h->shadow + (size_t)tile * ((size_t)h->d * kTileRows * 2);
+        KIRAG_CUDA_OK(cudaMemset2DAsync(tile_base + (size_t)rr * 128, (size_t)kTileRows * 128, 0, (size_t)(kTileRows - rr) * 128,
+                                        (size_t)(h->d / kKChunk), st));
+    }
+    unsigned bits[3] = {0, 0, 0};
+    KIRAG_CUDA_OK(cudaMemcpyAsync(bits, h->maxnorm2_bits, 12, cudaMemcpyDeviceToHost, st));
+    KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+    float m2[3];
+    memcpy(m2, bits, 12);
+    h->maxnorm = sqrtf(m2[0]);
+    h->maxerr = h->shadow ? sqrtf(m2[1]) : 0.f;
+    h->maxnorm_x = h->shadow ? sqrtf(m2[2]) : h->maxnorm;
+    h->ntotal = r0 + n;
+    return 0;
+}
+
 // ================================================================= C ABI ====
 extern "C" {
 
@@ -994,8 +1151,13 @@ int kirag_index_destroy(kirag_index_t* h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
-    if (h->master) cudaFree(h->master);
-    if (h->shadow) cudaFree(h->shadow);
+    if (h->use_vmm) {
+        h->vm_master.release();
+        h->vm_shadow.release();
+    } else {
+        if (h->master) cudaFree(h->master);
+        if (h->shadow) cudaFree(h->shadow);
+    }
     if (h->maxnorm2_bits) cudaFree(h->maxnorm2_bits);
     if (h->center) cudaFree(h->center);
     DevBuf* bufs[] = {&h->q_dev, &h->D_dev, &h->I_dev, &h->qshadow, &h->qnorm, &h->cand, &h->cnt, &h->tau, &h->tauk,
@@ -1030,28 +1192,7 @@ int kirag_index_add(kirag_index_t* h, const float* x, int64_t n, int x_is_device
     float* dst = h->master + h->ntotal * (int64_t)h->d;
     KIRAG_CUDA_OK(cudaMemcpyAsync(dst, x, (size_t)n * h->d * sizeof(float),
                                   x_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-    if (h->shadow && !h->center_decided && h->ntotal + n >= kCenterMinRows) {
-        // first time the index is large enough to tell: does the corpus have a large common component?
-        if (decide_center(h, h->ntotal + n, st)) return 1;
-        h->center_decided = true;
-        if (h->center && h->ntotal > 0) {  // rows converted before the decision: once more, now centred
-            KIRAG_CUDA_OK(cudaMemsetAsync(h->maxnorm2_bits, 0, 8, st));  // [0], [1] restart; [2] (max ||x||^2) stays
-            if (launch_convert_rows(h->master, h->ntotal, h->d, 0, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, nullptr,
-                                    h->center, nullptr, st)) return 1;
-        }
-    }
-    if (launch_convert_rows(dst, n, h->d, h->ntotal, h->shadow, kTileRows, h->maxnorm2_bits, nullptr, nullptr, h->center,
-                            nullptr, st)) return 1;
-    unsigned bits[3] = {0, 0, 0};
-    KIRAG_CUDA_OK(cudaMemcpyAsync(bits, h->maxnorm2_bits, 12, cudaMemcpyDeviceToHost, st));
-    KIRAG_CUDA_OK(cudaStreamSynchronize(st));
-    float m2[3];
-    memcpy(m2, bits, 12);
-    h->maxnorm = sqrtf(m2[0]);
-    h->maxerr = h->shadow ? sqrtf(m2[1]) : 0.f;
-    h->maxnorm_x = h->shadow ? sqrtf(m2[2]) : h->maxnorm;
-    h->ntotal += n;
-    return 0;
+    return finalize_rows(h, h->ntotal, n, st);
 }
 
 int64_t kirag_index_ntotal(const kirag_index_t* h) { return h ? h->ntotal : -1; }
@@ -1269,6 +1410,12 @@ int kirag_index_save(const kirag_index_t* h, const char* path) {
     return 0;
 }
 
+// faiss.read_index(path, IO_FLAG_MMAP) (retriever/index.py:73).  The corpus lives in HBM, so the file is streamed
+// there once: storage for exactly ntotal rows is mapped up front, the payload is read in 64 MB pieces into two
+// pinned buffers and copied while the next piece is being read (no per-piece synchronisation: the host only waits
+// for the piece that used the same buffer two pieces ago), then ONE convert pass builds the bf16 shadow.  The
+// IO_FLAG_MMAP the reference passes asks FAISS not to read the file eagerly; it has no meaning for a device-resident
+// index and is accepted and ignored.
 int kirag_index_load(const char* path, int device, kirag_index_t** out) {
     KIRAG_CHECK(path != nullptr && out != nullptr, "index_load: null argument");
     *out = nullptr;
@@ -1295,19 +1442,53 @@ int kirag_index_load(const char* path, int device, kirag_index_t** out) {
     }
     kirag_index_t* h = nullptr;
     if (kirag_index_create(d, KIRAG_METRIC_INNER_PRODUCT, device, &h)) { fclose(f); return 1; }
-    if (kirag_index_reserve(h, ntotal)) { fclose(f); kirag_index_destroy(h); return 1; }
-    std::vector<float> stage;
-    if (ntotal > 0) stage.resize(kIoChunkRows * (size_t)d);
-    for (int64_t r = 0; r < ntotal; r += (int64_t)kIoChunkRows) {
-        const int64_t rows = (ntotal - r < (int64_t)kIoChunkRows) ? (ntotal - r) : (int64_t)kIoChunkRows;
-        if (fread(stage.data(), 4, (size_t)rows * d, f) != (size_t)rows * d) {
-            fclose(f); kirag_index_destroy(h);
-            set_error("index_load: %s is truncated", path);
-            return 1;
+    if (ntotal == 0) { fclose(f); *out = h; return 0; }
+    DeviceGuard guard(device);
+    float* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    int rc = 1;
+    do {
+        if (!guard.ok) break;
+        if (kirag_index_reserve(h, ntotal)) break;
+        const size_t row_bytes = (size_t)d * 4;
+        int64_t piece_rows = (int64_t)(((size_t)64 << 20) / row_bytes);
+        if (piece_rows < 1) piece_rows = 1;
+        if (piece_rows > ntotal) piece_rows = ntotal;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { set_error("index_load: cudaStreamCreate failed"); break; }
+        bool alloc_ok = true;
+        for (int i = 0; i < 2; ++i)
+            alloc_ok = alloc_ok && cudaMallocHost((void**)&stage[i], (size_t)piece_rows * row_bytes) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!alloc_ok) { set_error("index_load: pinned staging buffers: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        bool io_ok = true;
+        int64_t piece = 0;
+        for (int64_t r = 0; r < ntotal && io_ok; r += piece_rows, ++piece) {
+            const int b = (int)(piece & 1);
+            const int64_t rows = (ntotal - r < piece_rows) ? (ntotal - r) : piece_rows;
+            if (piece >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) { io_ok = false; break; }  // buffer free again?
+            if (fread(stage[b], row_bytes, (size_t)rows, f) != (size_t)rows) {
+                set_error("index_load: %s is truncated", path);
+                io_ok = false;
+                break;
+            }
+            if (cudaMemcpyAsync(h->master + r * (int64_t)d, stage[b], (size_t)rows * row_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                cudaEventRecord(done[b], st) != cudaSuccess) {
+                set_error("index_load: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+                io_ok = false;
+            }
         }
-        if (kirag_index_add(h, stage.data(), rows, 0, nullptr)) { fclose(f); kirag_index_destroy(h); return 1; }
+        if (!io_ok) { cudaStreamSynchronize(st); break; }
+        if (finalize_rows(h, 0, ntotal, st)) break;
+        rc = 0;
+    } while (0);
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
     }
+    if (st) cudaStreamDestroy(st);
     fclose(f);
+    if (rc) { kirag_index_destroy(h); return 1; }
     *out = h;
     return 0;
 }

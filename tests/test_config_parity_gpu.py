@@ -30,7 +30,7 @@ def _free_device_memory():
     torch.cuda.empty_cache()
 
 
-def _make_index(n_rows):
+def _make_index(n_rows, reserve=True):
     from kirag_b200 import faiss_api
 
     _free_device_memory()
@@ -39,7 +39,8 @@ def _make_index(n_rows):
     if free < need:
         pytest.skip(f"needs {need >> 30} GiB of free HBM, {free >> 30} GiB available")
     ix = faiss_api.IndexFlatIP(1024, device=0)
-    ix.reserve(n_rows)
+    if reserve:
+        ix.reserve(n_rows)
     bench.build_shard(ix, 0, n_rows, torch.device("cuda", 0))
     assert ix.ntotal == n_rows
     return ix
@@ -89,7 +90,7 @@ def test_config2_5p2M_batch1024_top100():
         q, planted = _queries(ix, n, B, 16)
         sample = np.unique(np.concatenate([np.arange(16), np.linspace(16, B - 1, 64).astype(np.int64)]))
         D, I, st = _auto_vs_exact(ix, q, sample, n, "configs[2]")
-        assert st["n_fast"] + st["n_rescan"] + st["n_exact"] == B and st["n_fast"] >= B - 8, st
+        assert st["n_fast"] + st["n_rescan"] + st["n_exact"] + st["n_retry"] == B and st["n_fast"] >= B - 8, st
         assert np.array_equal(I[:16, 0], planted)
     finally:
         del ix
@@ -98,7 +99,10 @@ def test_config2_5p2M_batch1024_top100():
 
 @pytest.fixture(scope="module")
 def index_21m():
-    ix = _make_index(21_000_000)
+    # NO reserve: 21 add() calls of 2^20 rows, the way the reference's build path feeds an index
+    # (faiss_index_corpus.py:42-46: one index_data per 1M-row file, no reserve hook).  The index ends at 129 GB of
+    # the 180 GB, so growing by allocate-copy-free (two copies resident at once) could not get here.
+    ix = _make_index(21_000_000, reserve=False)
     yield ix
     del ix
     _free_device_memory()

@@ -506,3 +506,35 @@ def test_overflow_is_retried_with_the_gentle_schedule(fa, monkeypatch):
     D, I, st = ix.search_ex(xq, 32, path=AUTO)
     assert st["n_overflow"] >= 1 and st["n_retry"] >= 1, st
     assert_topk_parity(D, I, xb, xq, 32, what=f"retry {st}")
+
+
+def test_growth_without_virtual_memory_api_still_works(fa, monkeypatch):
+    """KIRAG_NO_VMM=1: the cudaMalloc + copy growth path (one buffer at a time) gives the same index."""
+    rng = np.random.default_rng(41)
+    xb, xq = unit_rows(rng, 30000, 128), unit_rows(rng, 5, 128)
+    ref = build(fa, xb)
+    D0, I0, _ = ref.search_ex(xq, 10)
+    # the switch is read once per process: exercise it in a child process
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from kirag_b200 import faiss_api\n"
+        "rng = np.random.default_rng(41)\n"
+        "x = rng.standard_normal((30000, 128)).astype(np.float32); x /= np.linalg.norm(x, axis=1, keepdims=True)\n"
+        "q = rng.standard_normal((5, 128)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)\n"
+        "ix = faiss_api.IndexFlatIP(128)\n"
+        "for a in range(0, 30000, 7000): ix.add(x[a:a + 7000].astype(np.float32))\n"
+        "D, I, st = ix.search_ex(q.astype(np.float32), 10)\n"
+        "np.save(sys.argv[1], I)\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "I.npy")
+        env = dict(os.environ, KIRAG_NO_VMM="1")
+        proc = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
+        assert proc.returncode == 0, proc.stderr[-2000:]
+        assert np.array_equal(np.load(out), I0)
