@@ -47,8 +47,10 @@ def parse_args():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--sweep", type=str, default=os.environ.get("KIRAG_BENCH_SWEEP", "1,32,256,1024,16384"),
                     help="extra query batch sizes reported in `sweep` (comma separated, '' for none)")
-    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the CPU sample (0: 1M for --impl reference, 256k for the cpu_baseline leg)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="rows of the CPU sample (0: 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the N=1 extras (other BASELINE configs, pooling, stress corpus, index I/O)")
     return ap.parse_args()
 
 
@@ -95,7 +97,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
@@ -104,14 +106,25 @@ class ClockSampler:
             try:
                 sm.append(float(parts[0]))
                 mx = float(parts[1])
+                pw.append(float(parts[2]))
             except ValueError:
                 continue
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
+        pw.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None}
+
+
+def workload_config(rows: int, batch: int, k: int) -> dict:
+    """The `config` of the bench line: identical for both arms (ours and --impl reference) at every N — the workload
+    is the same corpus, batch and k; how each arm runs it is described in `arm`."""
+    return {"workload": f"DPR psgs_w100-scale {rows}x{D_MODEL} fp32 corpus (BASELINE configs[3]), query batch {batch}, "
+                        f"exact inner-product top-{k}",
+            "rows": rows, "dim": D_MODEL, "batch": batch, "k": k,
+            "l2": "inputs (86 GB fp32 / 43 GB bf16) far larger than the 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------ reference arm ---
@@ -205,8 +218,9 @@ def run_reference(args):
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * args.batch / qps if qps > 0 else None, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DPR-scale {args.rows}x{D_MODEL} fp32 corpus, query batch {args.batch}, top-{args.k}",
-                   "rows": args.rows, "dim": D_MODEL, "batch": args.batch, "k": args.k},
+        "config": workload_config(args.rows, args.batch, args.k),
+        "arm": {"how": "FAISS-equivalent CPU flat search on all host cores, each step a bounded sample of the workload "
+                       "(see cpu_baseline.sample), throughput extrapolated linearly in rows"},
         "cpu_baseline": info,
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -291,13 +305,15 @@ def measure_batch(sh, lib, q_all, batch, k, steps, warmup, device, dist_ok, peak
         ach = flops_alg / (scan_ms_step * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"]}
-    # dram__bytes_read.sum + dram__bytes_write.sum of the scan launches of one step, from the committed
-    # `ncu --set full` capture of this very workload (profiles/r01b_scan_traffic.json); null otherwise
+    # dram__bytes_read.sum + dram__bytes_write.sum of the scan launches of one step.  DRAM counters cannot be read
+    # from inside a run, so this is the figure of the committed `ncu --set full` capture of this very command
+    # (profiles/r01b_scan_traffic.json, produced by tools/profile_r1c.sh) when the workload matches it, else null.
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01b_scan_traffic.json")
     if world == 1 and rows_total == 21_000_000 and k == 100 and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(str(batch), {}).get("dram_bytes_per_step")
-    roof.update({"traffic": traffic, "traffic_note": "bytes per step (all scan launches of one step), ncu capture",
+    roof.update({"traffic": traffic, "traffic_note": "bytes per step (all scan launches of one step); NOT measured in this "
+                 "run: read from the committed ncu --set full capture of the same command (profiles/r01b_scan_traffic.json)",
                  "kernel": ("scan_tc_pair_kernel<256,streamed>" if batch > 128 else "scan_tc_pair_kernel<128,resident>"
                             if batch > 64 else "scan_tc_kernel<%d,resident>" % (32 if batch <= 32 else 64)), "kernel_ms_per_step": scan_ms_step,
                  "kernel_share_of_step": scan_ms_step / ms if ms > 0 else None,
@@ -337,6 +353,224 @@ def parity_check(sh, q_all, batch, k, device, dist_ok, n_sample):
             "max_abs_score_diff": sdiff, "rows_ordered": ordered, "ids_in_range": in_range}
 
 
+# ------------------------------------------------- the other BASELINE configs, pooling, aligner, index I/O ---
+def _event_time_ms(fn, iters, warmup, device):
+    """Median and min of `iters` device-timed calls (CUDA events on the current stream), after `warmup` calls."""
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        times.append(e0.elapsed_time(e1))
+    times.sort()
+    return times[len(times) // 2], times[0]
+
+
+def _host_time_ms(fn, iters, warmup):
+    """Median wall time of a SYNCHRONOUS host call (host buffers in, host buffers out)."""
+    for _ in range(warmup):
+        fn()
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        fn()
+        times.append((time.perf_counter() - t0) * 1e3)
+    times.sort()
+    return times[len(times) // 2]
+
+
+def e5_like_rows(n, device, seed, common=0.85):
+    """Rows with a large common component, like E5 embeddings (random-pair cosine ~ common^2)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(9000)
+    mu = torch.nn.functional.normalize(torch.randn(1, D_MODEL, generator=g, device=device), dim=1)
+    g.manual_seed(seed)
+    x = torch.randn(n, D_MODEL, generator=g, device=device)
+    x = torch.nn.functional.normalize(x - (x @ mu.T) * mu, dim=1)
+    return torch.nn.functional.normalize(common * mu + (1.0 - common * common) ** 0.5 * x, dim=1)
+
+
+def bench_other_configs(peaks, device):
+    """BASELINE configs[0], [1], [2], [4] on one GPU, each through the faiss-shaped HOST call (host ndarray in,
+    host ndarrays out: IndexFlatIP.search, what retriever/index.py:47 calls) and with device-resident queries."""
+    import numpy as np
+    import torch
+
+    from kirag_b200 import faiss_api, scoring
+
+    out = []
+    hbm = peaks["hbm_gbs"] * 1e9
+    tc = peaks["bf16_tflops_sustained"] * 1e12
+    for name, rows, batch, k in (("configs[0] E5-shaped 100k x 1024, 1000 queries, top-10", 100_000, 1000, 10),
+                                 ("configs[1] 2Wiki-scale 430k x 1024, batch 64, top-20", 430_000, 64, 20),
+                                 ("configs[2] HotpotQA-scale 5.2M x 1024, batch 1024, top-100", 5_200_000, 1024, 100),
+                                 ("KiRAG call shape: 5.2M x 1024, 2 queries, top-10", 5_200_000, 2, 10)):
+        free, _ = torch.cuda.mem_get_info(device)
+        if free < rows * D_MODEL * 6 + (6 << 30):
+            out.append({"config": name, "skipped": f"{free >> 30} GiB free"})
+            continue
+        ix = faiss_api.IndexFlatIP(D_MODEL, device=device.index)
+        ix.reserve(rows)
+        build_shard(ix, 0, rows, device)
+        g = torch.Generator(device=device)
+        g.manual_seed(4321)
+        q = torch.nn.functional.normalize(torch.randn(batch, D_MODEL, generator=g, device=device), dim=1)
+        q_np = np.ascontiguousarray(q.cpu().numpy())
+        dev_ms, dev_min = _event_time_ms(lambda: ix.search_device(q, k), 10, 5, device)
+        host_ms = _host_time_ms(lambda: ix.search(q_np, k), 10, 3)
+        D, I = ix.search_device(q, k)
+        De, Ie = ix.search_device(q[:min(batch, 16)].contiguous(), k, path=1)
+        t_roof = max(rows * D_MODEL * 2 / hbm, 2.0 * batch * rows * D_MODEL / tc) * 1e3
+        out.append({"config": name, "rows": rows, "batch": batch, "k": k, "device_ms": dev_ms, "device_ms_min": dev_min,
+                    "host_call_ms": host_ms, "qps_device": batch / dev_ms * 1e3, "qps_host_call": batch / host_ms * 1e3,
+                    "roofline_ms": t_roof, "frac_of_roofline": t_roof / dev_ms,
+                    "parity_vs_exact": bool(torch.equal(I[:Ie.shape[0]], Ie) and torch.equal(D[:De.shape[0]], De)),
+                    "stats": dict(ix.last_stats)})
+        del ix
+        torch.cuda.empty_cache()
+    # configs[4]: aligner triple scoring, 256 chain queries x 50k candidate triples, top-20, through kirag_topk_ip
+    # (the transient candidate matrix is copied + converted on EVERY call: that is part of the measured time)
+    g = torch.Generator(device=device)
+    g.manual_seed(5)
+    T = torch.nn.functional.normalize(torch.randn(50_000, D_MODEL, generator=g, device=device), dim=1)
+    Q = torch.nn.functional.normalize(torch.randn(256, D_MODEL, generator=g, device=device), dim=1)
+    ms, ms_min = _event_time_ms(lambda: scoring.topk_inner_product(Q, T, 20), 20, 5, device)
+    ref_ms, _ = _event_time_ms(lambda: torch.topk(torch.matmul(Q, T.T), k=20, dim=1), 20, 5, device)
+    Dk, Ik = scoring.topk_inner_product(Q, T, 20)
+    ts, ti = torch.topk(torch.matmul(Q, T.T), k=20, dim=1)
+    out.append({"config": "configs[4] aligner: 256 chain queries x 50k triples, top-20 (kirag_topk_ip, per-call setup included)",
+                "rows": 50_000, "batch": 256, "k": 20, "device_ms": ms, "device_ms_min": ms_min,
+                "torch_matmul_topk_same_gpu_ms": ref_ms,
+                "ids_equal_torch_topk": float((Ik == ti).float().mean().item()),
+                "max_abs_score_diff": float((Dk - ts).abs().max().item())})
+    return out
+
+
+def bench_pooling(peaks, device):
+    """Mean-pool + L2-normalise epilogue on e5-large-v2-shaped hidden states [B, 512, 1024] (configs[4]); HBM roofline
+    over the algorithmic bytes sum_b len_b*H*s + B*S*8 + B*H*4.  Inputs (537 MB fp32) exceed the 126 MB L2."""
+    import torch
+
+    from kirag_b200 import pooling
+
+    out = []
+    for B, dtype, ragged in ((256, torch.float32, False), (256, torch.bfloat16, False), (256, torch.float32, True)):
+        S, H = 512, D_MODEL
+        g = torch.Generator(device=device)
+        g.manual_seed(777)
+        h = torch.randn(B, S, H, generator=g, device=device, dtype=torch.float32).to(dtype)
+        lens = torch.full((B,), S)
+        if ragged:
+            lens = torch.randint(1, S + 1, (B,), generator=torch.Generator().manual_seed(778))
+        m = (torch.arange(S)[None, :] < lens[:, None]).to(torch.int64).to(device)
+        alg = int(lens.sum()) * H * h.element_size() + B * S * 8 + B * H * 4
+        ms, ms_min = _event_time_ms(lambda: pooling.e5_embed(h, m), 20, 5, device)
+        ref = lambda: torch.nn.functional.normalize(
+            h.masked_fill(~m[..., None].bool(), 0.0).sum(dim=1) / m.sum(dim=1)[..., None], p=2, dim=1)
+        ref_ms, _ = _event_time_ms(ref, 10, 3, device)
+        err = float((pooling.e5_embed(h, m).float() - ref().float()).abs().max().item())
+        gbs = alg / (ms * 1e-3) / 1e9
+        out.append({"shape": [B, S, H], "dtype": str(dtype).replace("torch.", ""), "ragged": ragged, "ms": ms, "ms_min": ms_min,
+                    "algorithmic_bytes": alg, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"],
+                    "reference_aten_ms_same_gpu": ref_ms, "max_abs_diff_vs_reference_expression": err})
+        del h
+        torch.cuda.empty_cache()
+    return out
+
+
+def bench_stress(device, k):
+    """The certificate on an E5-like corpus (rows = normalize(0.85 mu + noise): random-pair cosine 0.72) against the
+    i.i.d. corpus of the same size: step time, certificate failures, second passes; answers checked against EXACT."""
+    import torch
+
+    from kirag_b200 import faiss_api
+
+    rows = 2_000_000
+    out = []
+    for kind in ("iid", "e5_like"):
+        ix = faiss_api.IndexFlatIP(D_MODEL, device=device.index)
+        ix.reserve(rows)
+        for c in range(0, rows, 500_000):
+            if kind == "iid":
+                g = torch.Generator(device=device)
+                g.manual_seed(600 + c)
+                x = torch.nn.functional.normalize(torch.randn(500_000, D_MODEL, generator=g, device=device), dim=1)
+            else:
+                x = e5_like_rows(500_000, device, 700 + c)
+            ix.add_device(x)
+            del x
+        for batch in (32, 1024):
+            if kind == "iid":
+                g = torch.Generator(device=device)
+                g.manual_seed(4321)
+                q = torch.nn.functional.normalize(torch.randn(batch, D_MODEL, generator=g, device=device), dim=1)
+            else:
+                q = e5_like_rows(batch, device, 4321)
+            ms, _ = _event_time_ms(lambda: ix.search_device(q, k), 10, 5, device)
+            D, I = ix.search_device(q, k)
+            st = dict(ix.last_stats)
+            De, Ie = ix.search_device(q[:16].contiguous(), k, path=1)
+            out.append({"corpus": kind, "rows": rows, "batch": batch, "ms_per_step": ms, "n_cert_fail": st["n_cert_fail"],
+                        "n_rescan": st["n_rescan"], "n_retry": st["n_retry"], "n_exact": st["n_exact"], "n_overflow": st["n_overflow"],
+                        "parity_vs_exact": bool(torch.equal(I[:16], Ie) and torch.equal(D[:16], De))})
+        del ix
+        torch.cuda.empty_cache()
+    return out
+
+
+def bench_index_io(device):
+    """faiss.write_index / faiss.read_index (retriever/index.py:62,73) on the largest corpus the scratch disk takes
+    (at most 4M rows = 16 GB): seconds and GB/s of the IxFI file, and the search result before == after."""
+    import shutil
+    import tempfile
+
+    import torch
+
+    from kirag_b200 import faiss_api
+
+    tmp = tempfile.mkdtemp(prefix="kirag_io_")
+    try:
+        free_disk = shutil.disk_usage(tmp).free
+        rows = 4_000_000
+        while rows * D_MODEL * 4 > free_disk * 0.5 and rows > 250_000:
+            rows //= 2
+        if rows * D_MODEL * 4 > free_disk * 0.5:
+            return {"skipped": f"{free_disk >> 30} GiB free on {tmp}"}
+        ix = faiss_api.IndexFlatIP(D_MODEL, device=device.index)
+        ix.reserve(rows)
+        build_shard(ix, 0, rows, device)
+        g = torch.Generator(device=device)
+        g.manual_seed(4321)
+        q = torch.nn.functional.normalize(torch.randn(8, D_MODEL, generator=g, device=device), dim=1)
+        D0, I0 = ix.search_device(q, 10)
+        path = os.path.join(tmp, "index.faiss")
+        t0 = time.perf_counter()
+        faiss_api.write_index(ix, path)
+        write_s = time.perf_counter() - t0
+        del ix
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        ix2 = faiss_api.read_index(path, faiss_api.IO_FLAG_MMAP, device=device.index)
+        load_s = time.perf_counter() - t0
+        D1, I1 = ix2.search_device(q, 10)
+        gb = rows * D_MODEL * 4 / 1e9
+        return {"rows": rows, "file_gb": gb, "write_s": write_s, "write_gbs": gb / write_s, "load_s": load_s,
+                "load_gbs": gb / load_s, "note": "load = read the IxFI file (page cache warm from the write) through two "
+                "pinned 64 MB buffers + one convert pass; includes building the bf16 shadow",
+                "same_results_after_reload": bool(torch.equal(I0, I1) and torch.equal(D0, D1))}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -362,7 +596,9 @@ def run_ours(args):
     k, B = args.k, args.batch
 
     sh = ShardedFlatIP(D_MODEL, args.rows, rank=rank, world_size=world, device=local_rank)
+    t_build = time.perf_counter()
     build_shard(sh.index, sh.lo, sh.hi, device)
+    build_s = time.perf_counter() - t_build
     gq = torch.Generator(device=device)
     gq.manual_seed(4321)
     sweep = [int(s) for s in args.sweep.split(",") if s.strip()] if args.sweep else []
@@ -417,9 +653,15 @@ def run_ours(args):
         if b == B:
             continue
         # short steps right after the power-capped headline phase: warm up longer so that the clocks have settled
+        sw_sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sw_sampler.start()
         r = measure_batch(sh, lib, q_all, b, k, max(3, min(args.steps, 5)), 10 if b <= 1024 else 3, device, dist_ok,
                           peaks, args.rows, world)
+        sw_clocks = sw_sampler.stop() if rank == 0 else None
         sweep_out.append({"batch": b, "qps": r["qps"], "ms_per_step": r["ms_per_step"],
+                          "sm_mhz": (sw_clocks or {}).get("sm_mhz"), "power_w": (sw_clocks or {}).get("power_w"),
+                          "throttle_reasons": (sw_clocks or {}).get("reasons"),
                           "roofline_bound": r["roofline"]["bound"], "roofline_frac": r["roofline"]["frac"],
                           "roofline_achieved": r["roofline"]["achieved"], "roofline_unit": r["roofline"]["unit"],
                           "n_fast": r["stats"].get("n_fast"), "n_exact": r["stats"].get("n_exact")})
@@ -440,27 +682,38 @@ def run_ours(args):
         # the CPU leg runs in its own process (own thread-pool settings), through the reference arm
         try:
             env = {k_: v for k_, v in os.environ.items() if not k_.endswith("_NUM_THREADS")}
-            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                                   "--warmup", "0", "--batch", str(B), "--k", str(k), "--rows", str(args.rows),
-                                   "--cpu-sample-rows", str(args.cpu_sample_rows or (1 << 18))],
+            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
+                                   "--warmup", "1", "--batch", str(B), "--k", str(k), "--rows", str(args.rows),
+                                   "--cpu-sample-rows", str(args.cpu_sample_rows or (1 << 20))],
                                   capture_output=True, text=True, timeout=600, env=env)
             cpu = json.loads(proc.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as exc:  # the baseline is a reported number, never a reason to lose the line
             cpu = {"value": None, "unit": "queries/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
                    "sample": f"failed: {exc}"}
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        # everything below needs the HBM the 21M-row index occupies
+        sh.index._destroy()
+        torch.cuda.empty_cache()
+        extras = {}
+        for name, fn in (("configs", lambda: bench_other_configs(peaks, device)), ("pooling", lambda: bench_pooling(peaks, device)),
+                         ("stress", lambda: bench_stress(device, k)), ("index_io", lambda: bench_index_io(device))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:  # an extra is a reported number, never a reason to lose the line
+                extras[name] = {"failed": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
     if rank == 0:
         line = {
             "metric": "QPS, exact IP top-%d over %dx%d" % (k, args.rows, D_MODEL),
             "value": head["qps"], "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16 filter + f32 rescoring", "data": "synthetic",
-            "config": {"workload": f"DPR-scale {args.rows}x{D_MODEL} corpus (configs[3]), query batch {B}, top-{k}, "
-                                   f"row-sharded over {world} GPU(s)",
-                       "rows": args.rows, "dim": D_MODEL, "batch": B, "k": k, "k_prime": 4 * k,
-                       "l2": "inputs (43 GB bf16 shadow) far larger than the 126 MB L2; no flush needed",
-                       "parallelism": (f"row-shard x{world} + " + ("fused NVLink peer-memory exchange+merge kernel"
-                                                                    if sh.peer is not None else "all_gather(k) + merge"))
-                       if world > 1 else "single GPU"},
+            "config": workload_config(args.rows, B, k),
+            "arm": {"k_prime": min(4 * k, 2048),
+                    "parallelism": (f"row-shard x{world} + " + ("fused NVLink peer-memory exchange+merge kernel"
+                                                                 if sh.peer is not None else "all_gather(k) + merge"))
+                    if world > 1 else "single GPU"},
             "roofline": head["roofline"],
             "cpu_baseline": cpu,
             "e2e": {"value": B / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
@@ -471,7 +724,12 @@ def run_ours(args):
             "parity": parity,
             "rank_diag": rank_diag,
             "sweep": sweep_out,
+            "build_s": build_s,
+            "build_note": f"rank 0's shard ({sh.hi - sh.lo} rows) from device-generated 2^20-row chunks through "
+                          "IndexFlatIP.add_device (fp32 copy + bf16 shadow convert), storage reserved up front",
         }
+        if extras is not None:
+            line.update(extras)
         emit(line)
     if dist_ok:
         sh.close()
