@@ -1281,11 +1281,15 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
     const char* force = getenv("KIRAG_DEBUG_BQ");
     if (force && *force) {
         // 32 / 64 / 128 / 256: single-CTA kernels (32 resident, the others streamed); 512: the 2-CTA kernel
-        // with 256-query tiles; 1128: the 2-CTA kernel with a resident 128-query tile; 1064: resident 64
+        // with 256-query tiles (2512 / 4512: two / four pairs per cluster with multicast query blocks); 1128: the
+        // 2-CTA kernel with a resident 128-query tile; 1064: resident 64
         plan.bq = atoi(force);
         plan.pair = 0;
+        plan.multi = 1;
         plan.resident = (plan.bq == 32) ? 1 : 0;
         if (plan.bq == 512) { plan.bq = 256; plan.pair = 1; }
+        if (plan.bq == 2512) { plan.bq = 256; plan.pair = 1; plan.multi = 2; }  // two pairs per cluster, multicast queries
+        if (plan.bq == 4512) { plan.bq = 256; plan.pair = 1; plan.multi = 4; }
         if (plan.bq == 1128) { plan.bq = 128; plan.pair = 1; plan.resident = 1; }
         if (plan.bq == 1064) { plan.bq = 64; plan.resident = 1; }
         plan.q_tile_rows = plan.pair ? plan.bq / 2 : plan.bq;

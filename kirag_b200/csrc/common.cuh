@@ -238,6 +238,7 @@ struct ScanTcPlan {
     int bq;           // query-tile width (UMMA N)
     int resident;     // 1: query tile stays in shared memory for the whole launch
     int pair;         // 1: 2-CTA (cta_group::2) kernel, M = 256 corpus rows per MMA
+    int multi;        // CTA pairs per cluster sharing multicast query blocks (streamed 2-CTA kernel only; 1, 2 or 4)
     int q_tile_rows;  // rows per tile of the query shadow layout (bq, or bq/2 for the pair kernel)
 };
 int scan_tc_supported(int d);

@@ -35,6 +35,7 @@ constexpr int kScanThreads = 192;
 constexpr int kMaxStages = 12;
 constexpr int kBlockBytes = kTileRows * 128;  // one [128 x 64] bf16 block = 16 KB
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kDefaultMulti = 1;  // pairs per cluster of the streamed 2-CTA kernel (KIRAG_SCAN_MULTI overrides)
 
 // ------------------------------------------------------------------ PTX ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -169,11 +170,22 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+// arrives on the barrier at this shared-memory offset in every CTA of the cluster whose rank bit is set in `mask`
+// (both CTAs of the pair; for the multi-pair kernel also the CTAs of the other pairs)
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// one bulk copy delivered to the same shared-memory offset of every CTA in `mask`; each destination's mbarrier at
+// the offset of `bar` receives the complete_tx of its copy
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t mask, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4, %5;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -614,9 +626,18 @@ template <int PQ, bool RES> struct PairCfg {
     static constexpr int kStageBytes = kBlockBytes + (RES ? 0 : kQHalfBytes);
 };
 
-template <int PQ, bool RES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<PQ>::kThreads, 1)
-scan_tc_pair_kernel(const ScanArgs a) {
+// NP = CTA pairs per cluster.  NP = 1 is the kernel described above.  NP > 1 (streamed variant only): the NP pairs
+// of a cluster work on different corpus tiles but on the SAME query tile and k-block at the same time, and the
+// 16 KB query half-block that the "same half" CTAs of all pairs need is fetched from L2 ONCE and multicast to them
+// (cp.async.bulk ... .multicast::cluster).  The streamed kernel is bound by the L2 -> SM fill path (32 KB per CTA
+// per 512 tensor cycles: the pipe is 84-85 % active with operands that all hit L2, ncu r01b / r2a), and half of
+// that traffic is the query operand; with NP pairs sharing it the fill drops to 16 + 16/NP KB per CTA and k-block.
+//   pair j's CTAs issue the query blocks of the k-blocks kc with kc % NP == j, for every pair;
+//   a stage may be refilled only when EVERY pair has consumed it: empty[s] collects one tcgen05.commit per pair
+//   (each commit is multicast to all 2 NP CTAs), so the pairs advance through the ring in lock-step.
+template <int PQ, bool RES, int NP>
+__device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
+    static_assert(NP == 1 || !RES, "query multicast is for the streamed variant");
     constexpr int kPairQ = PQ;
     constexpr int kPairHalfQ = PairCfg<PQ, RES>::kHalfQ;
     constexpr int kQHalfBytes = PairCfg<PQ, RES>::kQHalfBytes;
@@ -637,24 +658,33 @@ scan_tc_pair_kernel(const ScanArgs a) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int64_t pair = blockIdx.x >> 1;
-    const int64_t n_pairs = gridDim.x >> 1;
+    const uint32_t rank = cluster_ctarank();   // 0 .. 2 NP - 1
+    const uint32_t half = rank & 1u;            // 0: leader of its pair (issues the MMAs), 1: peer
+    const uint32_t pairc = rank >> 1;           // pair inside the cluster
+    const uint32_t leader = rank & ~1u;
+    constexpr int kCl = 2 * NP;                 // CTAs per cluster
+    constexpr uint16_t kMaskAll = (uint16_t)((1u << kCl) - 1u);
+    const uint16_t mask_pair = (uint16_t)(3u << leader);
+    uint16_t mask_half = 0;                     // the CTAs of every pair that stage the same query half as this one
+#pragma unroll
+    for (int j = 0; j < NP; ++j) mask_half |= (uint16_t)(1u << (2 * j + half));
+    const int64_t pair = blockIdx.x / kCl;       // work unit: the cluster
+    const int64_t n_pairs = gridDim.x / kCl;
     constexpr uint32_t kTmemCols = 2 * PQ;  // two accumulator stages of PQ columns
     const int n_qt = (int)((a.nq + kPairQ - 1) / kPairQ);
     // work item w = (pair of walk positions, 256-query tile), query tile fastest; every cluster takes
     // one contiguous, equally sized range of w, so small levels still occupy all SM pairs
-    const int64_t W = ((a.tile_hi - a.tile_lo + 1) / 2) * n_qt;
+    const int64_t W = ((a.tile_hi - a.tile_lo + kCl - 1) / kCl) * n_qt;
     const int64_t w_lo = W * pair / n_pairs;
     const int64_t w_hi = W * (pair + 1) / n_pairs;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(&full_bar[s], rank == 0 ? 2 : 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&full_bar[s], half == 0 ? 2 : 1);
+            mbar_init(&empty_bar[s], NP);  // one tcgen05.commit per pair of the cluster
         }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EpiCfg<kPairQ>::kWarps); }
-        mbar_init(q_bar, rank == 0 ? 2 : 1);
+        mbar_init(q_bar, half == 0 ? 2 : 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc2(tmem_holder, kTmemCols);
@@ -663,7 +693,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
-    // tiles of this level are taken two at a time: walk position 2*p + rank
+    // tiles of this level are taken 2 NP at a time: walk position 2*NP*p + rank
     if (warp == 0) {
         // =============================== producer ===============================
         if (lane == 0) {
@@ -672,7 +702,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
             if (a.q_dep) pdl_wait();
             if (RES) {  // the batch is one query tile: this CTA's half stays in shared memory for the whole launch
                 mbar_expect_tx(q_bar, (uint32_t)(KC * kQHalfBytes));
-                bulk_g2s(q_res, a.qshadow + (size_t)rank * ((size_t)a.d * kPairHalfQ * 2), (uint32_t)(KC * kQHalfBytes),
+                bulk_g2s(q_res, a.qshadow + (size_t)half * ((size_t)a.d * kPairHalfQ * 2), (uint32_t)(KC * kQHalfBytes),
                          q_bar, pol_q);
             }
             int s = 0;
@@ -680,15 +710,15 @@ scan_tc_pair_kernel(const ScanArgs a) {
             for (int64_t w = w_lo; w < w_hi; ++w) {
                 const int64_t p = w / n_qt;
                 const int qt = (int)(w - p * n_qt);
-                int64_t ti = a.tile_lo + 2 * p + rank;
-                if (ti >= a.tile_hi) ti = a.tile_hi - 1;  // odd tail: stage a valid tile, rows are masked later
+                int64_t ti = a.tile_lo + kCl * p + rank;
+                if (ti >= a.tile_hi) ti = a.tile_hi - 1;  // ragged tail: stage a valid tile, rows are masked later
                 const int64_t tile = (ti * a.tile_mult) % a.n_tiles;
                 const uint8_t* xsrc = a.shadow + (size_t)tile * ((size_t)a.d * kTileRows * 2);
-                // query shadow is stored in 128-row tiles: this CTA stages tile 2*qt + rank
-                const uint8_t* qsrc = a.qshadow + (size_t)(2 * qt + rank) * ((size_t)a.d * kPairHalfQ * 2);
+                // query shadow is stored in 128-row tiles: this CTA stages tile 2*qt + half
+                const uint8_t* qsrc = a.qshadow + (size_t)(2 * qt + half) * ((size_t)a.d * kPairHalfQ * 2);
                 const uint8_t* pfsrc = nullptr;  // the tile this CTA streams pf_tiles work items from now
                 if (a.pf_tiles > 0 && qt == 0 && (p + a.pf_tiles) * n_qt < w_hi) {
-                    int64_t pti = a.tile_lo + 2 * (p + a.pf_tiles) + rank;
+                    int64_t pti = a.tile_lo + kCl * (p + a.pf_tiles) + rank;
                     if (pti < a.tile_hi) pfsrc = a.shadow + (size_t)((pti * a.tile_mult) % a.n_tiles) * ((size_t)a.d * kTileRows * 2);
                 }
                 for (int kc = 0; kc < KC; ++kc) {
@@ -697,8 +727,13 @@ scan_tc_pair_kernel(const ScanArgs a) {
                     uint8_t* dst = stage_base + (size_t)s * kPairStageBytes;
                     mbar_expect_tx(&full_bar[s], (uint32_t)kPairStageBytes);
                     bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
-                    if (!RES)
-                        bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s], pol_q);
+                    if (!RES) {
+                        if (NP == 1)
+                            bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s], pol_q);
+                        else if ((uint32_t)(kc % NP) == pairc)  // this pair's turn: one L2 read for all NP pairs
+                            bulk_g2s_multicast(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s],
+                                               mask_half, pol_q);
+                    }
                     if (++s == NS) { s = 0; ph ^= 1u; }
                 }
             }
@@ -707,16 +742,16 @@ scan_tc_pair_kernel(const ScanArgs a) {
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            if (rank == 1) {
+            if (half == 1) {
                 // ============================= forwarder =============================
                 if (RES) {
-                    mbar_wait(q_bar, 0, 650);                       // this CTA's half of the query tile has landed
-                    mbar_arrive_cluster(map_to_rank(q_bar, 0));     // tell the leader
+                    mbar_wait(q_bar, 0, 650);                          // this CTA's half of the query tile has landed
+                    mbar_arrive_cluster(map_to_rank(q_bar, leader));   // tell the leader
                 }
                 for (int64_t w = w_lo; w < w_hi; ++w) {
                     for (int kc = 0; kc < KC; ++kc) {
                         mbar_wait(&full_bar[s], ph, 600 + s);               // this CTA's stage has landed
-                        mbar_arrive_cluster(map_to_rank(&full_bar[s], 0));  // tell the leader
+                        mbar_arrive_cluster(map_to_rank(&full_bar[s], leader));  // tell the leader
                         if (++s == NS) { s = 0; ph ^= 1u; }
                     }
                 }
@@ -741,10 +776,10 @@ scan_tc_pair_kernel(const ScanArgs a) {
                         for (int k4 = 0; k4 < 4; ++k4)
                             umma_bf16_2cta(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
                                            (kc | k4) ? 1u : 0u);
-                        umma_commit_2cta(&empty_bar[s]);
+                        umma_commit_2cta(&empty_bar[s], kMaskAll);  // every CTA of the cluster: the stage is free for this pair
                         if (++s == NS) { s = 0; ph ^= 1u; }
                     }
-                    umma_commit_2cta(&tmem_full[as]);
+                    umma_commit_2cta(&tmem_full[as], mask_pair);
                 }
             }
         }
@@ -753,8 +788,8 @@ scan_tc_pair_kernel(const ScanArgs a) {
         const int quad = warp & 3;
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         uint32_t leader_empty[2];
-        leader_empty[0] = map_to_rank(&tmem_empty[0], 0);
-        leader_empty[1] = map_to_rank(&tmem_empty[1], 0);
+        leader_empty[0] = map_to_rank(&tmem_empty[0], leader);
+        leader_empty[1] = map_to_rank(&tmem_empty[1], leader);
         constexpr int NG = EpiCfg<kPairQ>::kGroups;
         const int col0 = ((warp - 2) >> 2) * (NG * 32);
         uint32_t it = 0;
@@ -767,7 +802,7 @@ scan_tc_pair_kernel(const ScanArgs a) {
         for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
             const int64_t p = w / n_qt;
             const int qt = (int)(w - p * n_qt);
-            const int64_t ti = a.tile_lo + 2 * p + rank;
+            const int64_t ti = a.tile_lo + kCl * p + rank;
             const bool tile_ok = ti < a.tile_hi;
             const int64_t tile = ((tile_ok ? ti : a.tile_hi - 1) * a.tile_mult) % a.n_tiles;
             const int64_t row = tile * kTileRows + quad * 32 + lane;
@@ -799,6 +834,19 @@ scan_tc_pair_kernel(const ScanArgs a) {
         tc_fence_after();
         tmem_dealloc2(tmem_base, kTmemCols);
     }
+}
+
+template <int PQ, bool RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<PQ>::kThreads, 1)
+scan_tc_pair_kernel(const ScanArgs a) {
+    scan_pair_body<PQ, RES, 1>(a);
+}
+
+// NP pairs per cluster (cluster size 2 NP, given at launch): the streamed 256-query kernel with multicast query blocks
+template <int NP>
+__global__ void __launch_bounds__(EpiCfg<256>::kThreads, 1)
+scan_tc_multi_kernel(const ScanArgs a) {
+    scan_pair_body<256, false, NP>(a);
 }
 
 // ------------------------------------------------------------------ host ----
@@ -856,12 +904,18 @@ int scan_tc_pick(int64_t nq, int d, ScanTcPlan* plan) {
     KIRAG_CHECK(scan_tc_supported(d), "scan_tc: dimension %d is not supported (need a multiple of 64, <= 4096)", d);
     const int pair_ok = env_flag("KIRAG_SCAN_PAIR", 1) ? 1 : 0;
     plan->pair = 0;
+    plan->multi = 1;
     if (nq <= 32 && pick_stages(32, true, d) >= 4) { plan->bq = 32; plan->resident = 1; }
     else if (nq <= 64 && pick_stages(64, true, d) >= 4) { plan->bq = 64; plan->resident = 1; }  // 128 KB of queries + >= 4 stages
     else if (nq <= 64) { plan->bq = 64; plan->resident = 0; }
     else if (nq <= 128 && pair_ok && pair_stages<128, true>(d) >= 4) { plan->bq = 128; plan->resident = 1; plan->pair = 1; }
     else if (nq <= 128) { plan->bq = 128; plan->resident = 0; }
-    else { plan->bq = 256; plan->resident = 0; plan->pair = pair_ok; }
+    else {
+        plan->bq = 256; plan->resident = 0; plan->pair = pair_ok;
+        // pairs per cluster sharing one multicast copy of every query block (1: no sharing)
+        const int multi = env_flag("KIRAG_SCAN_MULTI", kDefaultMulti);
+        plan->multi = (pair_ok && (multi == 2 || multi == 4)) ? multi : 1;
+    }
     plan->q_tile_rows = plan->pair ? plan->bq / 2 : plan->bq;
     return 0;
 }
@@ -889,6 +943,51 @@ static int launch_scan_pair(const ScanArgs& args_in, int num_sms, cudaStream_t s
     return 0;
 }
 
+// cluster kernel with NP pairs per cluster: as many clusters as the GPU can hold at once (GPCs whose TPC count is not a
+// multiple of NP leave a TPC unused), each taking an equal contiguous range of (tile group, query tile) work items
+template <int NP>
+static int launch_scan_multi(const ScanArgs& args_in, int num_sms, cudaStream_t st) {
+    ScanArgs args = args_in;
+    const int ns = pair_stages<256, false>(args.d);
+    KIRAG_CHECK(ns >= 2, "scan_tc multi: no room for a shared-memory pipeline");
+    args.n_stages = ns;
+    const size_t smem = pair_fixed_bytes<256, false>(args.d) + (size_t)ns * PairCfg<256, false>::kStageBytes;
+    if (ensure_dynamic_smem(scan_tc_multi_kernel<NP>, kSmemLimit)) return 1;
+    constexpr int kCl = 2 * NP;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(EpiCfg<256>::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static int max_clusters[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per NP, queried once (one GPU model per process)
+    if (max_clusters[NP] == 0) {
+        cfg.gridDim = dim3((unsigned)(kCl * (num_sms / kCl)));
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, scan_tc_multi_kernel<NP>, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = num_sms / kCl / 2;  // conservative: co-residency of the whole grid is not required for correctness
+            if (n < 1) n = 1;
+        }
+        max_clusters[NP] = n;
+    }
+    int64_t clusters = ((args.tile_hi - args.tile_lo + kCl - 1) / kCl) * ((args.nq + 255) / 256);  // work items
+    if (clusters > max_clusters[NP]) clusters = max_clusters[NP];
+    if (clusters <= 0) return 0;
+    cfg.gridDim = dim3((unsigned)(kCl * clusters));
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    KIRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, scan_tc_multi_kernel<NP>, args));
+    KIRAG_LAUNCH_OK("scan_tc_multi_kernel");
+    return 0;
+}
+
 template <int BQ, bool RESIDENT>
 static int launch_scan_t(const ScanArgs& args_in, int num_sms, cudaStream_t st) {
     ScanArgs args = args_in;
@@ -907,6 +1006,8 @@ static int launch_scan_t(const ScanArgs& args_in, int num_sms, cudaStream_t st) 
 }
 
 static int launch_scan_args(const ScanArgs& args, const ScanTcPlan& plan, int num_sms, cudaStream_t st) {
+    if (plan.pair && plan.bq == 256 && !plan.resident && plan.multi == 2) return launch_scan_multi<2>(args, num_sms, st);
+    if (plan.pair && plan.bq == 256 && !plan.resident && plan.multi == 4) return launch_scan_multi<4>(args, num_sms, st);
     if (plan.pair && plan.bq == 256 && !plan.resident) return launch_scan_pair<256, false>(args, num_sms, st);
     if (plan.pair && plan.bq == 128 && plan.resident) return launch_scan_pair<128, true>(args, num_sms, st);
     if (plan.bq == 32 && plan.resident) return launch_scan_t<32, true>(args, num_sms, st);

@@ -538,3 +538,35 @@ def test_growth_without_virtual_memory_api_still_works(fa, monkeypatch):
         proc = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
         assert proc.returncode == 0, proc.stderr[-2000:]
         assert np.array_equal(np.load(out), I0)
+
+
+# ----------------------------------------- multi-pair cluster kernel (multicast query blocks) ---
+@pytest.mark.parametrize("code", ["512", "2512", "4512"])
+@pytest.mark.parametrize("n,d,nq", [(3000, 128, 260), (1100, 1024, 600), (129, 64, 257)])
+def test_multi_pair_cluster_kernel_scores_match_bf16_reference(fa, monkeypatch, code, n, d, nq):
+    """The streamed 2-CTA kernel with 1 / 2 / 4 CTA pairs per cluster (query blocks multicast to the pairs): dense
+    approximate scores equal the fp32-accumulated product of the bf16-rounded operands, ragged tile groups included."""
+    monkeypatch.setenv("KIRAG_DEBUG_BQ", code)
+    rng = np.random.default_rng(n + d + nq)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    got = build(fa, xb).debug_scores(xq)
+    ref = bf16_round(xb).astype(np.float64) @ bf16_round(xq).astype(np.float64).T
+    scale = np.linalg.norm(xb, axis=1)[:, None] * np.linalg.norm(xq, axis=1)[None, :]
+    assert np.max(np.abs(got - ref) / scale) < 2e-6
+
+
+@pytest.mark.parametrize("multi", ["2", "4"])
+def test_multi_pair_cluster_kernel_full_search(fa, monkeypatch, multi):
+    monkeypatch.setenv("KIRAG_SCAN_MULTI", multi)
+    rng = np.random.default_rng(50 + int(multi))
+    xb, xq = unit_rows(rng, 90000, 256), unit_rows(rng, 700, 256)
+    ix = build(fa, xb)
+    D, I, st = ix.search_ex(xq, 20, path=AUTO)
+    assert st["n_fast"] >= 690 and st["n_overflow"] == 0, st
+    De, Ie, _ = ix.search_ex(xq[:64], 20, path=EXACT)
+    assert np.array_equal(I[:64], Ie) and np.array_equal(D[:64], De)
+    xi, qi = int_corpus(rng, 30000, 128), int_corpus(rng, 300, 128)
+    D, I, st = build(fa, xi).search_ex(qi, 10, path=AUTO)
+    Do, Io = oracle.flat_ip_search_blas(xi, qi, 10, use_torch=True)
+    assert np.array_equal(I, Io) and np.array_equal(D, Do)
