@@ -796,9 +796,18 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
         Stash pend, cur;
         stash_clear(pend);
         pdl_wait();
-        float mytau[NG];
+        // Thresholds of this warp's columns: lane l holds tau of column g*32 + l.  They are fetched through L2 one
+        // work item AHEAD (the streamed variant changes query tile with every item): ncu r2a at B = 256 had the
+        // filter warps spend 52 % of their time on the in-loop tau loads — with the memory system saturated by the
+        // corpus stream an L2 hit takes ~3000 cycles, four of them per item made the filter, not HBM or the tensor
+        // pipe, the bound (22.6k cycles per item against 8.2k of MMA).
+        float mytau[NG], nxtau[NG];
+        {
+            const int qt0 = RES ? 0 : (int)(w_lo % n_qt);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) mytau[g] = RES ? __ldcg(a.tau + col0 + g * 32 + lane) : 0.f;  // RES: one query tile
+            for (int g = 0; g < NG; ++g)
+                mytau[g] = (w_lo < w_hi) ? __ldcg(a.tau + (int64_t)qt0 * kPairQ + col0 + g * 32 + lane) : 0.f;
+        }
         for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
             const int64_t p = w / n_qt;
             const int qt = (int)(w - p * n_qt);
@@ -809,15 +818,22 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
             const bool row_ok = tile_ok && row < a.n_rows;
             const uint32_t as = it & 1u;
             const uint32_t aph = (it >> 1) & 1u;
+            const int qt_next = (qt + 1 == n_qt) ? 0 : qt + 1;
+            const bool fetch = !RES && n_qt > 1 && w + 1 < w_hi;
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+                nxtau[g] = fetch ? __ldcg(a.tau + (int64_t)qt_next * kPairQ + col0 + g * 32 + lane) : mytau[g];
             mbar_wait(&tmem_full[as], aph, 500 + as);
             tc_fence_after();
             const uint32_t ebar = leader_empty[as];
-            filter_item<NG, RES>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
+            filter_item<NG, true>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
                             lane, cur, mytau, [=]() {
                                 tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive_cluster(ebar);
                             });
+#pragma unroll
+            for (int g = 0; g < NG; ++g) mytau[g] = nxtau[g];
             stash_store(a, pend);
             stash_reserve(a, cur);
             pend = cur;
