@@ -307,13 +307,14 @@ def measure_batch(sh, lib, q_all, batch, k, steps, warmup, device, dist_ok, peak
                 "frac": ach / peaks["bf16_tflops_sustained"]}
     # dram__bytes_read.sum + dram__bytes_write.sum of the scan launches of one step.  DRAM counters cannot be read
     # from inside a run, so this is the figure of the committed `ncu --set full` capture of this very command
-    # (profiles/r01b_scan_traffic.json, produced by tools/profile_r1c.sh) when the workload matches it, else null.
+    # (profiles/r02_scan_traffic.json, produced by tools/profile_r2b.sh) when the workload matches it, else null.
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01b_scan_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_scan_traffic.json")
     if world == 1 and rows_total == 21_000_000 and k == 100 and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(str(batch), {}).get("dram_bytes_per_step")
     roof.update({"traffic": traffic, "traffic_note": "bytes per step (all scan launches of one step); NOT measured in this "
-                 "run: read from the committed ncu --set full capture of the same command (profiles/r01b_scan_traffic.json)",
+                 "run (DRAM counters cannot be read from inside a run): read from the committed single-pass ncu capture of the "
+                 "same command (profiles/r02_scan_traffic.json, raw list profiles/r02_traffic_b4096.csv)",
                  "kernel": ("scan_tc_pair_kernel<256,streamed>" if batch > 128 else "scan_tc_pair_kernel<128,resident>"
                             if batch > 64 else "scan_tc_kernel<%d,resident>" % (32 if batch <= 32 else 64)), "kernel_ms_per_step": scan_ms_step,
                  "kernel_share_of_step": scan_ms_step / ms if ms > 0 else None,

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KIRAG_ABI_VERSION 4
+#define KIRAG_ABI_VERSION 5
 
 /* metric ids; only inner product is implemented, as only inner product is
  * ever constructed by the reference (retrieve.py:112, faiss_index_corpus.py:29) */
@@ -170,6 +170,18 @@ int kirag_index_search_finish(kirag_index_t* h, kirag_search_stats_t* stats, int
  * Lets a following kernel (the multi-GPU exchange) carry the flags along without a host round trip. */
 int kirag_index_search_flags(const kirag_index_t* h, const int** flags_dev);
 
+/* CUDA-graph replay of a captured kirag_index_search_async (KiRAG's own call shape is 1-2 queries per retrieval,
+ * knowledge_graph/models.py:1645: a dozen launches per search are then what a call costs on the host).  After the
+ * graph that contains the captured call has been launched on `stream`, this marks that search pending again, so that
+ * kirag_index_search_finish examines the certificate flags of the REPLAY and re-answers flagged queries in the
+ * captured D/I buffers.  Any other call on the handle completes a pending search first, as always. */
+int kirag_index_search_rearm(kirag_index_t* h, void* stream);
+
+/* A captured search has the index storage, the workspaces and the certificate constants baked into its kernel
+ * arguments.  The token changes whenever one of them does (rows added, a workspace grown by a larger call):
+ * replay a graph only while the token equals the one read right after the capture. */
+int kirag_index_state_token(const kirag_index_t* h, uint64_t* token);
+
 /* index.reconstruct_n(i0, n): copy rows [i0, i0+n) of the fp32 master out. */
 int kirag_index_reconstruct(const kirag_index_t* h, int64_t i0, int64_t n, float* out,
                             int out_is_device, void* stream);
@@ -229,9 +241,11 @@ int kirag_exchange_connect_ptrs(kirag_exchange_t* x, void* const* peer_buffers);
 void* kirag_exchange_buffer(kirag_exchange_t* x);
 /* D_loc/I_loc: this rank's per-shard result [nq,k] (device, rows sorted by (score desc, id asc), global
  * ids, padding id -1); D_out/I_out: the global top-k [nq,k] (device), identical on every rank.
- * Stream-ordered; the kernel spins (bounded, ~20 s) until every peer's call has delivered.  Every exchange of a
- * rank must be enqueued on the SAME stream (the first call fixes it; another stream is rejected): the buffers are
- * double-buffered by call parity, which is only safe if a rank's exchanges execute in call order. */
+ * Stream-ordered; the kernel spins (bounded, ~20 s) until every peer's call has delivered.  The buffers are
+ * double-buffered by call parity, which is only safe if a rank's exchanges EXECUTE in call order: calls on one
+ * stream are ordered by it, a call on another stream first waits (cudaStreamWaitEvent) for the previous exchange.
+ * The call parity (epoch) lives on the device, so a captured call can be replayed from a CUDA graph; whoever
+ * replays it orders the replays against the rank's other exchanges (e.g. by synchronising the replay stream). */
 int kirag_exchange_merge_topk(kirag_exchange_t* x, const float* D_loc, const int64_t* I_loc, int64_t nq, int k,
                               float* D_out, int64_t* I_out, void* stream);
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkirag_b200.so")
 
 # constants mirrored from the header
-ABI_VERSION = 4
+ABI_VERSION = 5
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 PATH_AUTO, PATH_EXACT, PATH_FAST = 0, 1, 2
@@ -68,6 +68,8 @@ SIGNATURES = {
     "kirag_index_search_async": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "kirag_index_search_finish": (c_int, [c_void_p, POINTER(SearchStats), POINTER(c_int64)]),
     "kirag_index_search_flags": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "kirag_index_search_rearm": (c_int, [c_void_p, c_void_p]),
+    "kirag_index_state_token": (c_int, [c_void_p, POINTER(ctypes.c_uint64)]),
     "kirag_index_reconstruct": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "kirag_index_save": (c_int, [c_void_p, c_char_p]),
     "kirag_index_load": (c_int, [c_char_p, c_int, POINTER(c_void_p)]),

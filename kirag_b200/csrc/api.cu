@@ -325,6 +325,8 @@ struct kirag_index {
     int* host_flags = nullptr;  // pinned: certificate read-back without a staging copy
     size_t host_flags_n = 0;
     PendingSearch pending;
+    PendingSearch captured;  // the asynchronous search most recently captured into a CUDA graph (kirag_index_search_rearm)
+    bool has_captured = false;
     cudaEvent_t pending_ev = nullptr;
 };
 
@@ -1238,6 +1240,44 @@ int kirag_index_search_async(kirag_index_t* h, const float* q, int64_t nq, int k
     p.nq = nq; p.k = k; p.id_offset = id_offset;
     p.qd = q; p.Dd = D; p.Id = I; p.st = st;
     p.active = true;
+    if (cap != cudaStreamCaptureStatusNone) {
+        h->captured = p;
+        h->has_captured = true;
+    }
+    return 0;
+}
+
+int kirag_index_search_rearm(kirag_index_t* h, void* stream) {
+    KIRAG_CHECK(h != nullptr, "search_rearm: null index");
+    KIRAG_CHECK(h->has_captured, "search_rearm: no asynchronous search has been captured on this index");
+    if (finish_pending(h, nullptr, nullptr)) return 1;
+    h->pending = h->captured;
+    h->pending.st = (cudaStream_t)stream;
+    h->pending.ev_recorded = false;
+    h->pending.launches0 = g_launches.load();
+    h->pending.active = true;
+    return 0;
+}
+
+// FNV-1a over everything a captured search has baked into its kernel arguments
+int kirag_index_state_token(const kirag_index_t* h, uint64_t* token) {
+    KIRAG_CHECK(h != nullptr && token != nullptr, "state_token: null argument");
+    uint64_t x = 1469598103934665603ULL;
+    auto mix = [&x](uint64_t v) {
+        for (int i = 0; i < 8; ++i) { x ^= (v >> (8 * i)) & 0xffu; x *= 1099511628211ULL; }
+    };
+    mix((uint64_t)h->ntotal);
+    mix((uint64_t)(uintptr_t)h->master);
+    mix((uint64_t)(uintptr_t)h->shadow);
+    mix((uint64_t)(uintptr_t)h->center);
+    uint32_t f[4];
+    memcpy(&f[0], &h->maxnorm, 4); memcpy(&f[1], &h->maxerr, 4); memcpy(&f[2], &h->maxnorm_x, 4); memcpy(&f[3], &h->center_norm, 4);
+    mix(((uint64_t)f[0] << 32) | f[1]);
+    mix(((uint64_t)f[2] << 32) | f[3]);
+    const DevBuf* bufs[] = {&h->qshadow, &h->qnorm, &h->cand, &h->cnt, &h->tau, &h->tauk, &h->overflow, &h->flags, &h->rescored};
+    for (const DevBuf* b : bufs) { mix((uint64_t)(uintptr_t)b->p); mix((uint64_t)b->bytes); }
+    mix((uint64_t)(uintptr_t)h->host_flags);
+    *token = x;
     return 0;
 }
 

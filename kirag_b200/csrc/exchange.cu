@@ -39,8 +39,8 @@ struct ExchangeArgs {
     int rank, G;
     int64_t nq;
     int k;
-    int parity;
-    int epoch;
+    const int* words;    // device: [0..1] OR of the carried flags by epoch parity, [2] the epoch of THIS call (advanced on
+                         // the device by exchange_tick_kernel, so that a captured CUDA graph can be replayed)
     size_t slot_bytes;   // capacity of one (parity, source rank) slot
     size_t flags_off;    // byte offset of the flag region
     size_t ids_off;      // byte offset of the id block inside a slot for this call (after nq*k scores)
@@ -59,11 +59,11 @@ struct ExchangeArgs {
     int* timeout_word;     // mapped pinned host word: set to 1 + source rank if a peer never delivered
 };
 
-__device__ __forceinline__ uint8_t* slot_ptr(const ExchangeArgs& a, int dst, int src) {
-    return a.peer[dst] + ((size_t)a.parity * a.G + src) * a.slot_bytes;
+__device__ __forceinline__ uint8_t* slot_ptr(const ExchangeArgs& a, int parity, int dst, int src) {
+    return a.peer[dst] + ((size_t)parity * a.G + src) * a.slot_bytes;
 }
-__device__ __forceinline__ int* flag_ptr(const ExchangeArgs& a, int dst, int src, int block) {
-    return reinterpret_cast<int*>(a.peer[dst] + a.flags_off) + ((size_t)a.parity * kMaxRanks + src) * kExchangeMaxBlocks + block;
+__device__ __forceinline__ int* flag_ptr(const ExchangeArgs& a, int parity, int dst, int src, int block) {
+    return reinterpret_cast<int*>(a.peer[dst] + a.flags_off) + ((size_t)parity * kMaxRanks + src) * kExchangeMaxBlocks + block;
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -95,6 +95,18 @@ __device__ __forceinline__ void group_barrier(int id, int n_threads) {
 
 constexpr int kExchangeThreads = 512;
 
+// Advances the epoch ON THE DEVICE (one thread) and clears the flag word of the new parity.  The epoch only has to
+// differ from the values two calls back; it is advanced in unsigned arithmetic so that a long-running server wraps
+// around instead of overflowing; 0 is the "never written" flag value and is skipped keeping the parity sequence
+// (... 0xffffffff odd, 2 even).  Keeping the epoch on the device (instead of passing it as a kernel argument) is
+// what makes an exchange replayable from a CUDA graph.
+__global__ void exchange_tick_kernel(int* words) {
+    unsigned e = (unsigned)words[2] + 1u;
+    if (e == 0u) e = 2u;
+    words[2] = (int)e;
+    words[e & 1u] = 0;
+}
+
 __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(const ExchangeArgs a) {
     extern __shared__ uint64_t xsmem[];
     const int G = a.G, k = a.k;
@@ -103,13 +115,16 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
     const int b = blockIdx.x, NB = gridDim.x;
     const int64_t q_lo = a.nq * b / NB, q_hi = a.nq * (b + 1) / NB;
     const int64_t e_lo = q_lo * k, e_hi = q_hi * k;
+    // epoch of this call: written by the tick kernel launched right before this one on the same stream
+    const int epoch = __ldcg(a.words + 2);
+    const int parity = (int)((unsigned)epoch & 1u);
 
     // ------------------------------------------------------------------ push ----
     // peers are visited in a rank-rotated order so that the G ranks do not all hit the same
     // destination at the same time; 16-byte stores when the rows allow it
     for (int p = 0; p < G; ++p) {
         const int dst = (a.rank + p) % G;
-        uint8_t* slot = slot_ptr(a, dst, a.rank);
+        uint8_t* slot = slot_ptr(a, parity, dst, a.rank);
         float* sd = reinterpret_cast<float*>(slot);
         int64_t* si = reinterpret_cast<int64_t*>(slot + a.ids_off);
         if (a.vec16) {
@@ -136,23 +151,23 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
     if (threadIdx.x < G) {
         // the barrier above ordered every thread's stores before this fence (cumulativity)
         __threadfence_system();
-        st_release_sys(flag_ptr(a, threadIdx.x, a.rank, b), a.epoch);
+        st_release_sys(flag_ptr(a, parity, threadIdx.x, a.rank, b), epoch);
     }
     // ------------------------------------------------------------------ wait ----
     __shared__ int s_timed_out;
     if (threadIdx.x == 0) s_timed_out = 0;
     __syncthreads();
     if (threadIdx.x < G) {
-        const int* f = flag_ptr(a, a.rank, threadIdx.x, b);
-        if (ld_acquire_sys(f) != a.epoch) {
+        const int* f = flag_ptr(a, parity, a.rank, threadIdx.x, b);
+        if (ld_acquire_sys(f) != epoch) {
             const long long t0 = clock64();
-            while (ld_acquire_sys(f) != a.epoch) {
+            while (ld_acquire_sys(f) != epoch) {
                 __nanosleep(64);
                 if (clock64() - t0 > 40000000000LL) {
                     // a peer never delivered (~20 s): report through the mapped host word and leave the kernel;
                     // the context stays usable and the host turns the word into an error status
                     printf("kirag exchange: rank %d block %d timed out waiting for rank %d (epoch %d, flag %d)\n",
-                           a.rank, b, (int)threadIdx.x, a.epoch, ld_acquire_sys(f));
+                           a.rank, b, (int)threadIdx.x, epoch, ld_acquire_sys(f));
                     *reinterpret_cast<volatile int*>(a.timeout_word) = 1 + (int)threadIdx.x;
                     __threadfence_system();
                     s_timed_out = 1;
@@ -170,8 +185,8 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
         int mine = 0;
         for (int64_t qq = q_lo + threadIdx.x; qq < q_hi; qq += blockDim.x)
             for (int g = 0; g < G; ++g)
-                mine |= __ldcg(reinterpret_cast<const int*>(slot_ptr(a, a.rank, g) + a.qflags_off) + qq);
-        if (__any_sync(0xffffffffu, mine != 0) && (threadIdx.x & 31) == 0) atomicOr(a.any_flag, 1);
+                mine |= __ldcg(reinterpret_cast<const int*>(slot_ptr(a, parity, a.rank, g) + a.qflags_off) + qq);
+        if (__any_sync(0xffffffffu, mine != 0) && (threadIdx.x & 31) == 0) atomicOr(a.any_flag + parity, 1);
     }
     // ----------------------------------------------------------------- merge ----
     // The CTA splits into n_groups thread groups; each merges one query at a time in its own slice of
@@ -195,7 +210,7 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
             group_barrier(1 + grp, gthreads);
             for (int i = gt; i < L; i += gthreads) {
                 const int g = i / k, j = i - g * k;
-                const uint8_t* slot = slot_ptr(a, a.rank, g);
+                const uint8_t* slot = slot_ptr(a, parity, a.rank, g);
                 const int64_t id = __ldcg(reinterpret_cast<const int64_t*>(slot + a.ids_off) + q * k + j);
                 uint32_t key = 0u;
                 if (id >= 0) key = score_key(__ldcg(reinterpret_cast<const float*>(slot) + q * k + j));
@@ -249,7 +264,7 @@ __global__ void __launch_bounds__(kExchangeThreads, 2) exchange_merge_kernel(con
         group_barrier(1 + grp, gthreads);
         for (int i = gt; i < L; i += gthreads) {
             const int g = i / k, j = i - g * k;
-            const uint8_t* slot = slot_ptr(a, a.rank, g);
+            const uint8_t* slot = slot_ptr(a, parity, a.rank, g);
             const int64_t id = __ldcg(reinterpret_cast<const int64_t*>(slot + a.ids_off) + q * k + j);
             uint32_t key = 0u;
             if (id >= 0) key = score_key(__ldcg(reinterpret_cast<const float*>(slot) + q * k + j));
@@ -299,13 +314,13 @@ struct kirag_exchange {
     uint8_t* peer[kMaxRanks] = {nullptr};
     bool opened[kMaxRanks] = {false};  // mapped with cudaIpcOpenMemHandle (to be closed)
     bool connected = false;
-    int epoch = 0;
     size_t qflags_off = 0;       // per-query certificate flags inside a slot
     int64_t qflags_cap = 0;      // queries the flag block of a slot can hold
-    int* any_dev = nullptr;      // [2] by parity
-    int* any_host = nullptr;     // pinned + mapped, [0..1] by parity: OR of the carried flags; [2]: time-out word
-    cudaStream_t stream = nullptr;  // the stream of the first exchange: every later call must use it (epoch
-    bool stream_set = false;        // double-buffering is only safe if a rank's calls execute in order)
+    int* any_dev = nullptr;      // [0..1] OR of the carried flags by parity, [2] epoch (device-side source of truth)
+    int* any_host = nullptr;     // pinned + mapped: [0..2] copy of any_dev after every exchange; [3]: time-out word
+    cudaStream_t stream = nullptr;  // stream of the previous exchange (epoch double-buffering is only safe if a rank's
+    bool stream_set = false;        // exchanges execute in call order: another stream first waits for last_ev)
+    cudaEvent_t last_ev = nullptr;  // recorded behind every exchange
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -362,8 +377,8 @@ int kirag_exchange_create(int device, int rank, int world, int64_t max_nq, int m
         if (prev >= 0) cudaSetDevice(prev);
         return 1;
     }
-    if (cudaMalloc((void**)&x->any_dev, 2 * sizeof(int)) != cudaSuccess ||
-        cudaMemset(x->any_dev, 0, 2 * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc((void**)&x->any_dev, 4 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(x->any_dev, 0, 4 * sizeof(int)) != cudaSuccess ||
         cudaHostAlloc((void**)&x->any_host, 4 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         set_error("exchange_create: allocating the flag words failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (x->any_dev) cudaFree(x->any_dev);
@@ -391,6 +406,7 @@ int kirag_exchange_destroy(kirag_exchange_t* x) {
     if (x->own) cudaFree(x->own);
     if (x->any_dev) cudaFree(x->any_dev);
     if (x->any_host) cudaFreeHost(x->any_host);
+    if (x->last_ev) cudaEventDestroy(x->last_ev);
     delete x;
     if (prev >= 0) cudaSetDevice(prev);
     return 0;
@@ -473,14 +489,22 @@ static int exchange_merge_impl(kirag_exchange_t* x, const float* D_loc, const in
     KIRAG_CHECK(D_loc && I_loc && D_out && I_out, "exchange_merge: null buffer");
     KIRAG_CHECK(!flags_loc || nq <= x->qflags_cap, "exchange_merge: nq=%lld exceeds the flag capacity %lld", (long long)nq,
                 (long long)x->qflags_cap);
-    // Epoch double-buffering assumes that this rank's exchanges execute in call order: they must all be enqueued
-    // on one stream (the first call fixes it).
-    KIRAG_CHECK(x->any_host[2] == 0, "exchange_merge: an earlier exchange timed out waiting for rank %d (a peer died or "
-                "skipped a call); this exchange object is no longer usable", x->any_host[2] - 1);
-    if (!x->stream_set) { x->stream = (cudaStream_t)stream; x->stream_set = true; }
-    KIRAG_CHECK(x->stream == (cudaStream_t)stream,
-                "exchange_merge: every exchange of a rank must be enqueued on the same stream (first call used %p, this one %p)",
-                (void*)x->stream, stream);
+    // Epoch double-buffering assumes that this rank's exchanges EXECUTE in call order.  Calls on one stream are
+    // ordered by the stream; a call on another stream first waits for the event recorded behind the previous
+    // exchange.  A call that is being captured into a CUDA graph can neither wait for outside work nor be waited
+    // for: whoever replays the graph orders the replays against this rank's other exchanges (ShardedFlatIP
+    // synchronises the replay stream at the end of every search).
+    KIRAG_CHECK(x->any_host[3] == 0, "exchange_merge: an earlier exchange timed out waiting for rank %d (a peer died or "
+                "skipped a call); this exchange object is no longer usable", x->any_host[3] - 1);
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream, &capturing);
+    if (capturing == cudaStreamCaptureStatusNone) {
+        if (!x->last_ev) KIRAG_CUDA_OK(cudaEventCreateWithFlags(&x->last_ev, cudaEventDisableTiming));
+        if (x->stream_set && x->stream != (cudaStream_t)stream)
+            KIRAG_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, x->last_ev, 0));
+        x->stream = (cudaStream_t)stream;
+        x->stream_set = true;
+    }
     DeviceGuardLite guard(x->device);
     ExchangeArgs a{};
     for (int g = 0; g < x->world; ++g) a.peer[g] = x->peer[g];
@@ -488,12 +512,7 @@ static int exchange_merge_impl(kirag_exchange_t* x, const float* D_loc, const in
     a.G = x->world;
     a.nq = nq;
     a.k = k;
-    // the epoch only has to differ from the values two calls back; it is advanced in unsigned arithmetic
-    // so that a long-running server wraps around instead of overflowing a signed int
-    x->epoch = (int)((unsigned)x->epoch + 1u);
-    if (x->epoch == 0) x->epoch = (int)2u;  // 0 is the "never written" flag value; keep the parity sequence (… 0xffffffff odd, 2 even)
-    a.epoch = x->epoch;
-    a.parity = (int)((unsigned)x->epoch & 1u);
+    a.words = x->any_dev;
     a.slot_bytes = x->slot_bytes;
     a.flags_off = x->flags_off;
     a.ids_off = align_up((size_t)nq * k * 4, 16);
@@ -515,14 +534,16 @@ static int exchange_merge_impl(kirag_exchange_t* x, const float* D_loc, const in
     if (smem > 48 * 1024 && ensure_dynamic_smem(exchange_merge_kernel, 96 * 1024)) return 1;
     a.flags_loc = flags_loc;
     a.qflags_off = x->qflags_off;
-    a.any_flag = x->any_dev + a.parity;
-    a.timeout_word = x->any_host + 2;  // mapped pinned memory: same address on the device under UVA
-    if (flags_loc) KIRAG_CUDA_OK(cudaMemsetAsync(a.any_flag, 0, sizeof(int), (cudaStream_t)stream));
+    a.any_flag = x->any_dev;
+    a.timeout_word = x->any_host + 3;  // mapped pinned memory: same address on the device under UVA
+    exchange_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(x->any_dev);
+    KIRAG_LAUNCH_OK("exchange_tick_kernel");
     exchange_merge_kernel<<<blocks, kExchangeThreads, smem, (cudaStream_t)stream>>>(a);
     KIRAG_LAUNCH_OK("exchange_merge_kernel");
-    if (flags_loc)
-        KIRAG_CUDA_OK(cudaMemcpyAsync(x->any_host + a.parity, a.any_flag, sizeof(int), cudaMemcpyDeviceToHost,
-                                      (cudaStream_t)stream));
+    // both flag words and the epoch they belong to: the host picks the word of the LAST executed exchange, also
+    // after a graph replay that it did not enqueue itself
+    KIRAG_CUDA_OK(cudaMemcpyAsync(x->any_host, x->any_dev, 3 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (capturing == cudaStreamCaptureStatusNone) KIRAG_CUDA_OK(cudaEventRecord(x->last_ev, (cudaStream_t)stream));
     return 0;
 }
 
@@ -539,11 +560,11 @@ int kirag_exchange_merge_topk_flags(kirag_exchange_t* x, const float* D_loc, con
 
 int kirag_exchange_last_any_flag(kirag_exchange_t* x) {
     if (!x) return -1;
-    if (x->any_host[2] != 0) {
-        set_error("exchange: timed out waiting for rank %d", x->any_host[2] - 1);
+    if (x->any_host[3] != 0) {
+        set_error("exchange: timed out waiting for rank %d", x->any_host[3] - 1);
         return -2;
     }
-    return x->any_host[(unsigned)x->epoch & 1u];
+    return x->any_host[(unsigned)x->any_host[2] & 1u];
 }
 
 }  // extern "C"

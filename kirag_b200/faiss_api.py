@@ -226,6 +226,65 @@ class IndexFlatIP:
         self._pending = None
         return int(changed.value)
 
+    # -- CUDA-graph replay of the asynchronous search (small query batches: launches are what a call costs) -----
+    def state_token(self) -> int:
+        """Changes whenever something a captured search baked into its kernel arguments does (rows added, a workspace
+        grown by a larger call): a graph is replayed only while the token is the one read after its capture."""
+        tok = ctypes.c_uint64(0)
+        _lib.check(self._lib.kirag_index_state_token(self._h, ctypes.byref(tok)), "state_token")
+        return int(tok.value)
+
+    def capture_search(self, nq: int, k: int, id_offset: int = 0, tail=None):
+        """Capture kirag_index_search_async for a fixed (nq, k) into a CUDA graph.  `tail(D, I)` (optional) is called
+        inside the capture with the search's output tensors and may enqueue more work on the capture stream (the
+        multi-GPU exchange); what it returns is kept in the result.  Returns a dict with the static buffers
+        (`q` to fill, `D`/`I` results), the graph, its stream and the state token."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        q = torch.nn.functional.normalize(torch.randn((nq, self.d), dtype=torch.float32, device=dev), dim=1)
+        self.search_device(q, k, id_offset=id_offset)  # warm the workspaces: the capture itself must not allocate
+        torch.cuda.synchronize(dev)
+        stream = torch.cuda.Stream(device=dev)
+        graph = torch.cuda.CUDAGraph()
+        extra = None
+        # nothing executes during the capture (in particular no cross-GPU rendez-vous of `tail`): ranks of a sharded
+        # index may (re)capture independently of each other
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(graph, stream=stream):
+                D, I = self.search_device_async(q, k, id_offset=id_offset)
+                if tail is not None:
+                    extra = tail(D, I)
+        self.finish()  # the capture left a (never executed) pending search behind
+        return {"q": q, "D": D, "I": I, "graph": graph, "stream": stream, "extra": extra, "token": self.state_token(),
+                "nq": nq, "k": k, "id_offset": id_offset}
+
+    def replay_search(self, cap) -> None:
+        """Launch a captured search on its stream and mark it pending (finish() completes it)."""
+        cap["graph"].replay()
+        _lib.check(self._lib.kirag_index_search_rearm(self._h, ctypes.c_void_p(cap["stream"].cuda_stream)), "search_rearm")
+        self._pending = (cap["q"], cap["D"], cap["I"])
+
+    def search_device_graph(self, q, k: int, id_offset: int = 0):
+        """search_device for small batches through a cached CUDA graph per (nq, k): one graph launch instead of a
+        dozen kernel launches.  The returned tensors are the graph's static output buffers: they are overwritten by the
+        next call with the same (nq, k)."""
+        import torch
+
+        q = self._own_tensor(q, "search_device_graph")
+        key = (int(q.shape[0]), int(k), int(id_offset))
+        cache = self.__dict__.setdefault("_graphs", {})
+        cap = cache.get(key)
+        if cap is None or cap["token"] != self.state_token():
+            cap = cache[key] = self.capture_search(key[0], key[1], id_offset=key[2])
+        cur = torch.cuda.current_stream(q.device)
+        cap["stream"].wait_stream(cur)
+        with torch.cuda.stream(cap["stream"]):
+            cap["q"].copy_(q, non_blocking=True)
+            self.replay_search(cap)
+        self.finish()  # synchronises the graph's stream, verifies the certificates, re-answers flagged queries
+        return cap["D"], cap["I"]
+
     def debug_scores(self, x) -> np.ndarray:
         """Dense approximate (bf16 tcgen05) scores [ntotal, nq] — test hook."""
         x = np.ascontiguousarray(x, dtype=np.float32)

@@ -258,6 +258,39 @@ class ShardedFlatIP:
         D_loc, I_loc = self.search_local(q, k, path=path)
         return self.exchange_merge(D_loc, I_loc)
 
+    def search_graph(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """search() for small query batches with the whole chain — local search, exchange+merge kernel, flag
+        read-back — replayed from ONE CUDA graph per (nq, k): a graph launch and a stream synchronisation are all the
+        host does per call (KiRAG's own shape is 1-2 queries per retrieval, knowledge_graph/models.py:1645).  Every
+        rank must call it with the same shapes (SPMD).  The returned tensors are the graph's static output buffers
+        (overwritten by the next call with the same shape)."""
+        nq = int(q.shape[0])
+        if not (self.peer is not None and self.world_size > 1 and self.peer.fits(nq, k) and 0 < nq <= 1024
+                and hasattr(self.index, "capture_search")):
+            return self.search(q, k)
+        cache = self.__dict__.setdefault("_graphs", {})
+        key = (nq, int(k))
+        cap = cache.get(key)
+        if cap is None or cap["token"] != self.index.state_token():
+            # capturing executes nothing (no rendez-vous with the peers), so a rank may recapture on its own
+            def tail(D_loc, I_loc):
+                return self.peer.merge(D_loc, I_loc, self.index.pending_flags_ptr())
+
+            cap = cache[key] = self.index.capture_search(nq, int(k), id_offset=self.lo, tail=tail)
+        cur = torch.cuda.current_stream(q.device)
+        cap["stream"].wait_stream(cur)
+        with torch.cuda.stream(cap["stream"]):
+            cap["q"].copy_(q, non_blocking=True)
+            self.index.replay_search(cap)
+            cap["stream"].synchronize()
+            redo = self.peer.any_flag()
+            self.index.finish()
+            D, I = cap["extra"]
+            if redo:
+                D, I = self.peer.merge(cap["D"], cap["I"])
+                cap["stream"].synchronize()
+        return D, I
+
     def exchange_merge(self, D_loc: torch.Tensor, I_loc: torch.Tensor,
                        lists_sorted: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
         """Per-rank results [nq,k] with globally unique ids (padding id -1) -> the global top-k on every rank.

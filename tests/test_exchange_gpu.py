@@ -155,9 +155,10 @@ def test_exchange_carries_certificate_flags_to_every_rank():
         ranks.close()
 
 
-def test_exchange_rejects_a_second_stream():
-    """Epoch double-buffering is only safe if a rank's exchanges execute in call order: the first call fixes the
-    stream, another one is an error (not a silent race)."""
+def test_exchange_orders_calls_across_streams_and_replays_from_a_graph():
+    """Epoch double-buffering is only safe if a rank's exchanges execute in call order: a call on another stream
+    waits for the previous exchange (event), and because the epoch lives on the device a captured exchange can be
+    replayed from a CUDA graph any number of times."""
     from kirag_b200 import _lib
 
     lib = _lib.load()
@@ -170,10 +171,22 @@ def test_exchange_rejects_a_second_stream():
         s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
         args = (ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()), 2, 4, ctypes.c_void_p(Do.data_ptr()),
                 ctypes.c_void_p(Io.data_ptr()))
-        assert lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s1.cuda_stream)) == 0
-        assert lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s2.cuda_stream)) != 0
-        assert "same stream" in _lib.last_error()
-        assert lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s1.cuda_stream)) == 0
+        for st in (s1, s2, s1, s2, s2, s1):
+            _lib.check(lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(st.cuda_stream)), "merge")
+        torch.cuda.synchronize()
+        assert torch.equal(Io, I)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s1):
+            with torch.cuda.graph(graph, stream=s1):
+                _lib.check(lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s1.cuda_stream)), "merge (captured)")
+            for trial in range(5):  # both parities, several times
+                I.add_(100)
+                Io.zero_()
+                graph.replay()
+                s1.synchronize()
+                assert torch.equal(Io, I), trial
+                assert lib.kirag_exchange_last_any_flag(h) == 0
+        _lib.check(lib.kirag_exchange_merge_topk(h, *args, ctypes.c_void_p(s2.cuda_stream)), "merge after replays")
         torch.cuda.synchronize()
         assert torch.equal(Io, I)
     finally:

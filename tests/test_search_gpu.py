@@ -426,6 +426,43 @@ def test_async_search_is_cuda_graph_capturable(fa):
     assert ix.finish() == 0  # the captured call left a pending search behind: complete it
 
 
+def test_graph_replayed_search_equals_the_plain_call_and_recaptures_when_the_index_changes(fa):
+    """IndexFlatIP.search_device_graph: one CUDA-graph launch per call.  Same ids and scores as search_device on new
+    query contents; adding rows changes the state token and forces a new capture; queries whose certificate fails
+    in a replay are re-answered by finish() like in the plain call."""
+    import torch
+
+    rng = np.random.default_rng(31)
+    xb = unit_rows(rng, 90000, 128)
+    ix = build(fa, xb[:60000])
+    for trial in range(3):
+        q = torch.from_numpy(unit_rows(rng, 5, 128)).cuda()
+        Dg, Ig = ix.search_device_graph(q, 10)
+        Dg, Ig = Dg.clone(), Ig.clone()
+        Dp, Ip = ix.search_device(q, 10)
+        assert torch.equal(Ig, Ip) and torch.equal(Dg, Dp), trial
+        assert_topk_parity(Dg.cpu().numpy(), Ig.cpu().numpy(), xb[:60000], q.cpu().numpy(), 10, what=f"graph {trial}")
+    assert len(ix._graphs) == 1
+    tok = ix.state_token()
+    ix.add(xb[60000:])
+    assert ix.state_token() != tok
+    q = torch.from_numpy(unit_rows(rng, 5, 128)).cuda()
+    Dg, Ig = ix.search_device_graph(q, 10)
+    assert_topk_parity(Dg.cpu().numpy(), Ig.cpu().numpy(), xb, q.cpu().numpy(), 10, what="after add")
+    # certificate failures inside a replay: tight clusters (rank k and rank 4k nearly tie)
+    centers = unit_rows(rng, 64, 128)
+    xc = centers[rng.integers(0, 64, 60000)] + 0.01 * unit_rows(rng, 60000, 128)
+    xc = (xc / np.linalg.norm(xc, axis=1, keepdims=True)).astype(np.float32)
+    ic = build(fa, xc)
+    for trial in range(2):
+        qc = torch.from_numpy((centers[trial * 4:trial * 4 + 4] + 0.01 * unit_rows(rng, 4, 128)).astype(np.float32)).cuda()
+        Dg, Ig = ic.search_device_graph(qc, 10)
+        st = ic.last_stats
+        assert st["n_cert_fail"] + st["n_overflow"] >= 1, st
+        De, Ie = ic.search_device(qc, 10, path=EXACT)
+        assert torch.equal(Ig, Ie) and torch.equal(Dg, De), trial
+
+
 def test_k_above_512_stays_on_the_filter_path(fa):
     """k' = min(4k, 2048): k up to 2048 is answered by the tcgen05 filter path, not by the fp32 scan."""
     rng = np.random.default_rng(23)

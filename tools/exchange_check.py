@@ -42,6 +42,10 @@ def main():
             Dp, Ip = peer.search(q, k)
         Dn, In = nccl.search(q, k)
         same = bool(torch.equal(Ip, In) and torch.equal(Dp, Dn))
+        if nq <= 256:  # the whole chain replayed from one CUDA graph (twice: capture + replay, both parities)
+            for rep in range(3):
+                Dg, Ig = peer.search_graph(q, k)
+                same = same and bool(torch.equal(Ig, Ip) and torch.equal(Dg, Dp))
         if rank == 0:
             Df, If = full.search_device(q, k)
             same = same and bool(torch.equal(Ip, If) and torch.equal(Dp, Df))
