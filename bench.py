@@ -584,7 +584,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from kirag_b200 import _build, _lib
-    from kirag_b200.sharded import ShardedFlatIP
+    from kirag_b200.sharded import ShardedFlatIP, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -602,7 +602,16 @@ def run_ours(args):
     peaks = load_peaks()
     k, B = args.k, args.batch
 
-    sh = ShardedFlatIP(D_MODEL, args.rows, rank=rank, world_size=world, device=local_rank)
+    # N > 1: a strong-scaling step is paced by the slowest GPU, and the GPUs of one box sit at different power-capped
+    # clocks (rank_diag of the r01 / r02 runs: 18.0 ... 19.9 ms of local search on equal shards).  Every rank's speed
+    # is measured on a small probe index (all ranks at the same time, ~2 s, outside every timed region) and the row
+    # ranges are made proportional to it.  KIRAG_BENCH_EQUAL_SHARDS=1 keeps equal shards.
+    weights = None
+    if dist_ok and os.environ.get("KIRAG_BENCH_EQUAL_SHARDS", "0") != "1":
+        from kirag_b200.sharded import measure_rank_weights
+
+        weights = measure_rank_weights(D_MODEL, local_rank, nq=min(B, 4096), k=k)
+    sh = ShardedFlatIP(D_MODEL, args.rows, rank=rank, world_size=world, device=local_rank, weights=weights)
     t_build = time.perf_counter()
     build_shard(sh.index, sh.lo, sh.hi, device)
     build_s = time.perf_counter() - t_build
@@ -632,7 +641,9 @@ def run_ours(args):
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         rank_diag = {"local_search_ms_per_rank": [round(float(x.item()), 3) for x in allt],
-                     "exchange_merge_ms": exch_ms}
+                     "exchange_merge_ms": exch_ms,
+                     "shard_weights": None if weights is None else [round(w, 4) for w in weights],
+                     "shard_rows": [b_ - a_ for a_, b_ in (shard_range(args.rows, world, r_, weights) for r_ in range(world))]}
 
     # end to end through the reference-facing call with HOST buffers (rank-local shard; for N > 1 the
     # exchange + merge are included through the device path and the final result is copied out)
@@ -663,7 +674,9 @@ def run_ours(args):
         sw_sampler = ClockSampler(local_rank)
         if rank == 0:
             sw_sampler.start()
-        r = measure_batch(sh, lib, q_all, b, k, max(3, min(args.steps, 5)), 10 if b <= 1024 else 3, device, dist_ok,
+        # a step of a small batch takes ~1 ms on an 8-GPU shard: time enough of them (>= ~0.1 s) for a stable figure
+        sw_steps = 100 if b <= 128 else 20 if b <= 1024 else max(3, min(args.steps, 5))
+        r = measure_batch(sh, lib, q_all, b, k, sw_steps, 10 if b <= 1024 else 3, device, dist_ok,
                           peaks, args.rows, world)
         sw_clocks = sw_sampler.stop() if rank == 0 else None
         sweep_out.append({"batch": b, "qps": r["qps"], "ms_per_step": r["ms_per_step"],
@@ -671,7 +684,7 @@ def run_ours(args):
                           "throttle_reasons": (sw_clocks or {}).get("reasons"),
                           "roofline_bound": r["roofline"]["bound"], "roofline_frac": r["roofline"]["frac"],
                           "roofline_achieved": r["roofline"]["achieved"], "roofline_unit": r["roofline"]["unit"],
-                          "n_fast": r["stats"].get("n_fast"), "n_exact": r["stats"].get("n_exact")})
+                          "n_fast": r["stats"].get("n_fast"), "n_exact": r["stats"].get("n_exact"), "steps": sw_steps})
 
     # parity where the numbers are quoted (outside every timed region; every rank takes part for N > 1)
     checks = [parity_check(sh, q_all, B, k, device, dist_ok, 64)]

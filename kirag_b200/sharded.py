@@ -34,12 +34,75 @@ import torch.distributed as dist
 from . import _lib
 
 
-def shard_range(n_total: int, world_size: int, rank: int) -> Tuple[int, int]:
-    """Contiguous row range of `rank`: ceil-sized shards, the last ones may be short/empty."""
-    per = (n_total + world_size - 1) // world_size
-    lo = min(rank * per, n_total)
-    hi = min(lo + per, n_total)
-    return lo, hi
+def shard_range(n_total: int, world_size: int, rank: int, weights=None) -> Tuple[int, int]:
+    """Contiguous row range of `rank`.  Default: ceil-sized shards, the last ones may be short/empty.  With
+    `weights` (one positive number per rank, the same list on every rank): ranges proportional to the weights,
+    boundaries rounded to whole 128-row tiles — a strong-scaling step is paced by its slowest GPU, and the GPUs of
+    one box run at different power-capped clocks (measure_rank_weights)."""
+    if weights is None:
+        per = (n_total + world_size - 1) // world_size
+        lo = min(rank * per, n_total)
+        hi = min(lo + per, n_total)
+        return lo, hi
+    assert len(weights) == world_size and all(w > 0 for w in weights), "one positive weight per rank"
+    total = float(sum(weights))
+    bounds = [0]
+    acc = 0.0
+    for w in weights[:-1]:
+        acc += float(w)
+        b = int(round(acc / total * n_total / 128.0)) * 128
+        bounds.append(min(max(b, bounds[-1]), n_total))
+    bounds.append(n_total)
+    return bounds[rank], bounds[rank + 1]
+
+
+def measure_rank_weights(d: int, device: int, group=None, nq: int = 4096, k: int = 100, rows: int = 1 << 20,
+                         seconds: float = 2.0):
+    """Relative search speed of every rank's GPU (SPMD: all ranks call it together): each rank builds the same
+    small probe index and runs the tensor-bound search for `seconds` at the same time as its peers (the power and
+    thermal situation of the real job); returns the list of rates normalised to mean 1 (identical on every rank),
+    ready for ShardedFlatIP(..., weights=...)."""
+    import time
+
+    from .faiss_api import IndexFlatIP
+
+    dev = torch.device("cuda", device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(20241)
+    ix = IndexFlatIP(d, device=device)
+    ix.reserve(rows)
+    chunk = 1 << 18
+    for r0 in range(0, rows, chunk):
+        ix.add_device(torch.nn.functional.normalize(torch.randn(min(chunk, rows - r0), d, generator=g, device=dev), dim=1))
+    q = torch.nn.functional.normalize(torch.randn(nq, d, generator=g, device=dev), dim=1)
+    for _ in range(3):
+        ix.search_device(q, k)
+    torch.cuda.synchronize(dev)
+    if dist.is_initialized():
+        dist.barrier(group=group)
+    times = []
+    t_end = time.perf_counter() + seconds
+    while time.perf_counter() < t_end or len(times) < 5:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ix.search_device(q, k)
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1))
+    del ix
+    torch.cuda.empty_cache()
+    tail = sorted(times[len(times) // 2:])  # second half: clocks have settled under the power cap
+    ms = tail[len(tail) // 2]
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    t = torch.tensor([1.0 / ms], dtype=torch.float64, device=dev)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allt, t, group=group)
+    else:
+        allt = [t]
+    rates = [float(x.item()) for x in allt]
+    mean = sum(rates) / len(rates)
+    return [r / mean for r in rates]
 
 
 def merge_topk_device(D_all: torch.Tensor, I_all: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -170,13 +233,14 @@ class ShardedFlatIP:
     def __init__(self, d: int, n_total: int, rank: Optional[int] = None, world_size: Optional[int] = None,
                  device: Optional[int] = None, group=None,
                  local_index=None, merge_fn: Optional[Callable] = None, exchange: Optional[str] = None,
-                 max_nq: int = 16384, max_k: int = 128):
+                 max_nq: int = 16384, max_k: int = 128, weights=None):
         self.d = d
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world_size = dist.get_world_size(group) if world_size is None else world_size
         self.n_total = int(n_total)
-        self.lo, self.hi = shard_range(self.n_total, self.world_size, self.rank)
+        self.weights = None if weights is None else [float(w) for w in weights]
+        self.lo, self.hi = shard_range(self.n_total, self.world_size, self.rank, self.weights)
         if local_index is None:
             from .faiss_api import IndexFlatIP
 

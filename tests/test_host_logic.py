@@ -13,6 +13,24 @@ from oracle import oracle
 from tests.helpers import int_corpus
 
 
+def test_weighted_shard_ranges_partition_the_rows_in_proportion():
+    """Speed-weighted shards (ShardedFlatIP(weights=...)): contiguous, disjoint, complete, tile-aligned inner
+    boundaries, sizes proportional to the weights; equal weights ~ equal shards."""
+    n = 21_000_000
+    w = [1.07, 1.0, 1.01, 0.98, 0.96, 1.0, 0.95, 0.95]
+    spans = [shard_range(n, 8, r, w) for r in range(8)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 == b0 and a0 <= a1 and b0 % 128 == 0
+    for (lo, hi), wi in zip(spans, w):
+        assert abs((hi - lo) - n * wi / sum(w)) <= 256
+    eq = [shard_range(n, 8, r, [1.0] * 8) for r in range(8)]
+    assert all(abs((hi - lo) - n / 8) <= 256 for lo, hi in eq)
+    # degenerate: fewer rows than ranks * tile
+    tiny = [shard_range(300, 4, r, [1, 1, 1, 1]) for r in range(4)]
+    assert tiny[0][0] == 0 and tiny[-1][1] == 300 and all(a1 == b0 for (_, a1), (b0, _) in zip(tiny, tiny[1:]))
+
+
 def test_shard_ranges_partition_the_rows():
     for n in (0, 1, 7, 8, 9, 1000, 21_000_000):
         for G in (1, 2, 4, 8):

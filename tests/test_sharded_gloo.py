@@ -38,7 +38,7 @@ def _merge(D_all, I_all):
     return torch.from_numpy(D), torch.from_numpy(I)
 
 
-def _worker(rank, world, port, n, d, nq, k, ret):
+def _worker(rank, world, port, n, d, nq, k, ret, weights=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -47,7 +47,7 @@ def _worker(rank, world, port, n, d, nq, k, ret):
 
         rng = np.random.default_rng(11)
         xb, xq = int_corpus(rng, n, d), int_corpus(rng, nq, d)
-        sh = ShardedFlatIP(d, n, local_index=_LocalOracleIndex(d), merge_fn=_merge)
+        sh = ShardedFlatIP(d, n, local_index=_LocalOracleIndex(d), merge_fn=_merge, weights=weights)
         sh.add_shard(xb[sh.lo:sh.hi])
         D, I = sh.search(torch.from_numpy(xq), k)
         D1, I1 = oracle.flat_ip_search(xb, xq, k)
@@ -64,6 +64,17 @@ def test_sharded_search_world_size_2(n, k):
     s.close()
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(2, port, n, 16, 4, k, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_sharded_search_world_size_2_with_speed_weighted_shards():
+    """Unequal row ranges (ShardedFlatIP(weights=...), what bench.py uses at N > 1): same global result."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, port, 1000, 16, 4, 9, ret, [1.3, 0.7]), nprocs=2, join=True)
     assert ret[0] and ret[1]
 
 
