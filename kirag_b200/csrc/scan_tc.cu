@@ -236,7 +236,8 @@ struct ScanArgs {
     int* cnt;          // [nq]
     int cap;
     int n_stages;
-    int x_policy;      // L2 policy of corpus blocks that are re-read per query tile: 1 normal, 2 evict_last
+    int x_policy;      // L2 policy of corpus blocks that are re-read per query tile: 1 normal, 2 evict_last,
+                       // 3 evict_last + evict_first on the last read
     int q_dep;         // 1: the query shadow is written by the kernel right before this one in the chain
                        // (level 0): the producer must pdl_wait() too; 0: only the filter warps wait
     int pf_tiles;      // L2 prefetch distance of the corpus stream, in corpus tiles of this CTA (0: off)
@@ -716,7 +717,8 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
     if (warp == 0) {
         // =============================== producer ===============================
         if (lane == 0) {
-            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy == 2 ? policy_evict_last() : policy_evict_normal());
+            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy >= 2 ? policy_evict_last() : policy_evict_normal());
+            const uint64_t pol_x_last = policy_evict_first();
             const uint64_t pol_q = policy_evict_last();
             if (a.q_dep) pdl_wait();
             if (RES) {  // the batch is one query tile: this CTA's half stays in shared memory for the whole launch
@@ -740,12 +742,15 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
                     int64_t pti = a.tile_lo + kCl * (p + a.pf_tiles) + rank;
                     if (pti < a.tile_hi) pfsrc = a.shadow + (size_t)((pti * a.tile_mult) % a.n_tiles) * ((size_t)a.d * kTileRows * 2);
                 }
+                // x_policy 3: the LAST read of a corpus block (last query tile) demotes it to evict_first, so that dead
+                // tiles, not live ones, make room for the next tiles
+                const uint64_t pol_xw = (a.x_policy == 3 && n_qt > 1 && qt == n_qt - 1) ? pol_x_last : pol_x;
                 for (int kc = 0; kc < KC; ++kc) {
                     if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
                     mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
                     uint8_t* dst = stage_base + (size_t)s * kPairStageBytes;
                     mbar_expect_tx(&full_bar[s], (uint32_t)kPairStageBytes);
-                    bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
+                    bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_xw);
                     if (!RES) {
                         if (NP == 1)
                             bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s], pol_q);
@@ -1075,7 +1080,11 @@ int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshado
     args.cap = cap;
     args.dump = nullptr;
     args.dump_ld = 0;
-    args.x_policy = env_flag("KIRAG_X_POLICY", 2);  // evict_last measured ~2% faster at batch 4096 (less HBM re-read)
+    // corpus blocks that are re-read once per query tile: evict_last, and evict_first on their LAST read so that dead
+    // tiles make room instead of live ones.  DRAM reads of a 21M-row step at batch 4096 (43.0 GB algorithmic; single-pass
+    // ncu, gpurun_out/r2w, r2x): evict_normal 78.6 GB, evict_last 61.8 GB, with the demotion 54.3 GB; time unchanged
+    // (DRAM is at 6 %).
+    args.x_policy = env_flag("KIRAG_X_POLICY", 3);
     args.pf_tiles = env_flag("KIRAG_PF_TILES", 0);
     return launch_scan_args(args, plan, num_sms, st);
 }
