@@ -74,6 +74,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
         }
     }
 }
+// One lane of the (converged) warp.  The producer / MMA / forwarder warps run their loops with ALL lanes on warp-uniform
+// values and only predicate the issuing instructions on this: ptxas then keeps smem addresses, descriptors and
+// barrier addresses in uniform registers.  With a single active thread (`if (lane == 0)`) it cannot prove uniformity
+// and wraps every tcgen05.mma / bulk copy in an ELECT + 5x R2UR.BROADCAST waterfall: ncu (r2m, B = 4096) showed the MMA
+// thread busy issuing ~115 instructions per k-block for ~480 of the 512 tensor cycles the four MMAs take.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -508,14 +522,15 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
 
     if (warp == 0) {
         // =============================== producer ===============================
-        if (lane == 0) {
-            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy == 2 ? policy_evict_last() : policy_evict_normal());
+        {
+            const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy >= 2 ? policy_evict_last() : policy_evict_normal());
             const uint64_t pol_q = policy_evict_last();
             if (a.q_dep) pdl_wait();  // level 0: the query shadow is being written by the previous kernel
-            if (RESIDENT) {
+            if (RESIDENT && elect_one()) {
                 mbar_expect_tx(q_bar, (uint32_t)(KC * kQBlockBytes));
                 bulk_g2s(q_res, a.qshadow, (uint32_t)(KC * kQBlockBytes), q_bar, pol_q);
             }
+            __syncwarp();
             int s = 0;
             uint32_t ph = 0;
             for (int64_t w = w_lo; w < w_hi; ++w) {
@@ -530,20 +545,23 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
                     pfsrc = a.shadow + (size_t)ptile * ((size_t)a.d * kTileRows * 2);
                 }
                 for (int kc = 0; kc < KC; ++kc) {
-                    if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
                     mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
                     uint8_t* dst = stage_base + (size_t)s * stage_bytes;
-                    mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                    bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
-                    if (!RESIDENT)
-                        bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQBlockBytes, kQBlockBytes, &full_bar[s], pol_q);
+                    if (elect_one()) {
+                        if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
+                        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                        bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_x);
+                        if (!RESIDENT)
+                            bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQBlockBytes, kQBlockBytes, &full_bar[s], pol_q);
+                    }
+                    __syncwarp();
                     if (++s == NS) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================= MMA ==================================
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = make_idesc_bf16(kTileRows, BQ);
             if (RESIDENT) mbar_wait(q_bar, 0, 200);
             int s = 0;
@@ -562,16 +580,19 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
                     const uint32_t qa = RESIDENT ? smem_u32(q_res + (size_t)kc * kQBlockBytes) : xa + kBlockBytes;
                     const uint64_t da = make_sw128_desc(xa);
                     const uint64_t db = make_sw128_desc(qa);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        // +32 bytes (two 16-byte units) per K=16 step inside the 128-byte swizzle row
-                        umma_bf16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
-                                  (kc | k4) ? 1u : 0u);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            // +32 bytes (two 16-byte units) per K=16 step inside the 128-byte swizzle row
+                            umma_bf16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
+                                      (kc | k4) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+                        if (kc == KC - 1) umma_commit(&tmem_full[as]);  // accumulator complete
                     }
-                    umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+                    __syncwarp();
                     if (++s == NS) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(&tmem_full[as]);  // accumulator complete
             }
         }
     } else {
@@ -716,16 +737,18 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
     // tiles of this level are taken 2 NP at a time: walk position 2*NP*p + rank
     if (warp == 0) {
         // =============================== producer ===============================
-        if (lane == 0) {
+        // (all lanes run the warp-uniform loop, one elected lane issues: see elect_one)
+        {
             const uint64_t pol_x = (n_qt == 1) ? policy_evict_first() : (a.x_policy >= 2 ? policy_evict_last() : policy_evict_normal());
             const uint64_t pol_x_last = policy_evict_first();
             const uint64_t pol_q = policy_evict_last();
             if (a.q_dep) pdl_wait();
-            if (RES) {  // the batch is one query tile: this CTA's half stays in shared memory for the whole launch
+            if (RES && elect_one()) {  // the batch is one query tile: this CTA's half stays in shared memory for the whole launch
                 mbar_expect_tx(q_bar, (uint32_t)(KC * kQHalfBytes));
                 bulk_g2s(q_res, a.qshadow + (size_t)half * ((size_t)a.d * kPairHalfQ * 2), (uint32_t)(KC * kQHalfBytes),
                          q_bar, pol_q);
             }
+            __syncwarp();
             int s = 0;
             uint32_t ph = 0;
             for (int64_t w = w_lo; w < w_hi; ++w) {
@@ -746,36 +769,41 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
                 // tiles, not live ones, make room for the next tiles
                 const uint64_t pol_xw = (a.x_policy == 3 && n_qt > 1 && qt == n_qt - 1) ? pol_x_last : pol_x;
                 for (int kc = 0; kc < KC; ++kc) {
-                    if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
                     mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
                     uint8_t* dst = stage_base + (size_t)s * kPairStageBytes;
-                    mbar_expect_tx(&full_bar[s], (uint32_t)kPairStageBytes);
-                    bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_xw);
-                    if (!RES) {
-                        if (NP == 1)
-                            bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s], pol_q);
-                        else if ((uint32_t)(kc % NP) == pairc)  // this pair's turn: one L2 read for all NP pairs
-                            bulk_g2s_multicast(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s],
-                                               mask_half, pol_q);
+                    if (elect_one()) {
+                        if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
+                        mbar_expect_tx(&full_bar[s], (uint32_t)kPairStageBytes);
+                        bulk_g2s(dst, xsrc + (size_t)kc * kBlockBytes, kBlockBytes, &full_bar[s], pol_xw);
+                        if (!RES) {
+                            if (NP == 1)
+                                bulk_g2s(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s], pol_q);
+                            else if ((uint32_t)(kc % NP) == pairc)  // this pair's turn: one L2 read for all NP pairs
+                                bulk_g2s_multicast(dst + kBlockBytes, qsrc + (size_t)kc * kQHalfBytes, kQHalfBytes, &full_bar[s],
+                                                   mask_half, pol_q);
+                        }
                     }
+                    __syncwarp();
                     if (++s == NS) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             int s = 0;
             uint32_t ph = 0;
             if (half == 1) {
                 // ============================= forwarder =============================
                 if (RES) {
                     mbar_wait(q_bar, 0, 650);                          // this CTA's half of the query tile has landed
-                    mbar_arrive_cluster(map_to_rank(q_bar, leader));   // tell the leader
+                    if (elect_one()) mbar_arrive_cluster(map_to_rank(q_bar, leader));   // tell the leader
+                    __syncwarp();
                 }
                 for (int64_t w = w_lo; w < w_hi; ++w) {
                     for (int kc = 0; kc < KC; ++kc) {
                         mbar_wait(&full_bar[s], ph, 600 + s);               // this CTA's stage has landed
-                        mbar_arrive_cluster(map_to_rank(&full_bar[s], leader));  // tell the leader
+                        if (elect_one()) mbar_arrive_cluster(map_to_rank(&full_bar[s], leader));  // tell the leader
+                        __syncwarp();
                         if (++s == NS) { s = 0; ph ^= 1u; }
                     }
                 }
@@ -796,14 +824,17 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
                         const uint32_t xa = smem_u32(stage_base + (size_t)s * kPairStageBytes);
                         const uint64_t da = make_sw128_desc(xa);
                         const uint64_t db = make_sw128_desc(RES ? smem_u32(q_res + (size_t)kc * kQHalfBytes) : xa + kBlockBytes);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)
-                            umma_bf16_2cta(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
-                                           (kc | k4) ? 1u : 0u);
-                        umma_commit_2cta(&empty_bar[s], kMaskAll);  // every CTA of the cluster: the stage is free for this pair
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                umma_bf16_2cta(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
+                                               (kc | k4) ? 1u : 0u);
+                            umma_commit_2cta(&empty_bar[s], kMaskAll);  // every CTA of the cluster: the stage is free for this pair
+                            if (kc == KC - 1) umma_commit_2cta(&tmem_full[as], mask_pair);
+                        }
+                        __syncwarp();
                         if (++s == NS) { s = 0; ph ^= 1u; }
                     }
-                    umma_commit_2cta(&tmem_full[as], mask_pair);
                 }
             }
         }
