@@ -607,10 +607,14 @@ def run_ours(args):
     # is measured on a small probe index (all ranks at the same time, ~2 s, outside every timed region) and the row
     # ranges are made proportional to it.  KIRAG_BENCH_EQUAL_SHARDS=1 keeps equal shards.
     weights = None
+    measured_weights = None
     if dist_ok and os.environ.get("KIRAG_BENCH_EQUAL_SHARDS", "0") != "1":
         from kirag_b200.sharded import measure_rank_weights
 
         weights = measure_rank_weights(D_MODEL, local_rank, nq=min(B, 4096), k=k)
+        measured_weights = list(weights)
+        if max(weights) / min(weights) < 1.03:  # within the noise of the probe: equal shards
+            weights = None
     sh = ShardedFlatIP(D_MODEL, args.rows, rank=rank, world_size=world, device=local_rank, weights=weights)
     t_build = time.perf_counter()
     build_shard(sh.index, sh.lo, sh.hi, device)
@@ -643,6 +647,7 @@ def run_ours(args):
         rank_diag = {"local_search_ms_per_rank": [round(float(x.item()), 3) for x in allt],
                      "exchange_merge_ms": exch_ms,
                      "shard_weights": None if weights is None else [round(w, 4) for w in weights],
+                     "measured_rank_speeds": None if measured_weights is None else [round(w, 4) for w in measured_weights],
                      "shard_rows": [b_ - a_ for a_, b_ in (shard_range(args.rows, world, r_, weights) for r_ in range(world))]}
 
     # end to end through the reference-facing call with HOST buffers (rank-local shard; for N > 1 the
