@@ -428,12 +428,21 @@ def bench_other_configs(peaks, device):
         q_np = np.ascontiguousarray(q.cpu().numpy())
         dev_ms, dev_min = _event_time_ms(lambda: ix.search_device(q, k), 10, 5, device)
         host_ms = _host_time_ms(lambda: ix.search(q_np, k), 10, 3)
+        # the whole asynchronous chain replayed from ONE CUDA graph (wall clock per call, stream sync included)
+        graph_ms, graph_same = None, None
+        if batch <= 1024:
+            Dg, Ig = ix.search_device_graph(q, k)
+            Dp, Ip = ix.search_device(q, k)
+            graph_same = bool(torch.equal(Dg, Dp) and torch.equal(Ig, Ip))
+            graph_ms = _host_time_ms(lambda: ix.search_device_graph(q, k), 20, 5)
+        dev_call_ms = _host_time_ms(lambda: ix.search_device(q, k), 20, 5)
         D, I = ix.search_device(q, k)
         stats = dict(ix.last_stats)
         De, Ie = ix.search_device(q[:min(batch, 16)].contiguous(), k, path=1)
         t_roof = max(rows * D_MODEL * 2 / hbm, 2.0 * batch * rows * D_MODEL / tc) * 1e3
         out.append({"config": name, "rows": rows, "batch": batch, "k": k, "device_ms": dev_ms, "device_ms_min": dev_min,
-                    "host_call_ms": host_ms, "qps_device": batch / dev_ms * 1e3, "qps_host_call": batch / host_ms * 1e3,
+                    "host_call_ms": host_ms, "device_call_wall_ms": dev_call_ms, "graph_call_wall_ms": graph_ms,
+                    "graph_equals_plain": graph_same, "qps_device": batch / dev_ms * 1e3, "qps_host_call": batch / host_ms * 1e3,
                     "roofline_ms": t_roof, "frac_of_roofline": t_roof / dev_ms,
                     "parity_vs_exact": bool(torch.equal(I[:Ie.shape[0]], Ie) and torch.equal(D[:De.shape[0]], De)),
                     "stats": stats})

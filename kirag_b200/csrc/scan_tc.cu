@@ -31,7 +31,6 @@
 
 namespace kirag {
 
-constexpr int kScanThreads = 192;
 constexpr int kMaxStages = 12;
 constexpr int kBlockBytes = kTileRows * 128;  // one [128 x 64] bf16 block = 16 KB
 constexpr int kSmemLimit = 227 * 1024;
@@ -267,31 +266,19 @@ struct ScanArgs {
 // counters of ALL groups are bumped by NG independent atomic instructions (one round trip in
 // total, not one per group), and pass 2 re-reads from TMEM only the groups that have survivors
 // and stores (score, row) at the reserved slots.
-// TAU_SHFL: the thresholds of this warp's columns live in registers (lane l holds tau of column
-// g*32 + l, loaded once per query tile through L2) and are broadcast by shuffles.  Otherwise they are
-// read per group with vector loads through L2.  tau must not be read through L1 / the non-coherent
-// path: it is rewritten by the previous kernel of a programmatically chained launch, and an L2 load in
-// the loop costs the HBM-bound variants 16% (the accumulator is held while the load is in flight).
-template <bool TAU_SHFL>
+// The thresholds of this warp's columns live in registers (lane l holds tau of column g*32 + l, fetched through L2
+// once per query tile, one work item ahead) and are broadcast by shuffles.  tau must not be read through L1 / the
+// non-coherent path: it is rewritten by the previous kernel of a programmatically chained launch; and it must not be
+// loaded inside the filter loop at all: with the memory system saturated by the corpus stream an L2 hit takes ~3000
+// cycles while the accumulator is held (16 % on the HBM-bound variants in round 1, the bound of the streamed 2-CTA
+// kernel at the ridge in round 2).
 __device__ __forceinline__ uint32_t pass_mask(const ScanArgs& a, const uint32_t (&v)[32], int64_t q0, int64_t row,
                                               bool row_ok, float mytau) {
     uint32_t pass = 0;
-    if (TAU_SHFL) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float t = __shfl_sync(0xffffffffu, mytau, c);
-            pass |= (__uint_as_float(v[c]) >= t ? 1u : 0u) << c;
-        }
-    } else {
-        const float4* tp = reinterpret_cast<const float4*>(a.tau + q0);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 t = __ldcg(tp + c4);
-            pass |= (__uint_as_float(v[c4 * 4 + 0]) >= t.x ? 1u : 0u) << (c4 * 4 + 0);
-            pass |= (__uint_as_float(v[c4 * 4 + 1]) >= t.y ? 1u : 0u) << (c4 * 4 + 1);
-            pass |= (__uint_as_float(v[c4 * 4 + 2]) >= t.z ? 1u : 0u) << (c4 * 4 + 2);
-            pass |= (__uint_as_float(v[c4 * 4 + 3]) >= t.w ? 1u : 0u) << (c4 * 4 + 3);
-        }
+    for (int c = 0; c < 32; ++c) {
+        const float t = __shfl_sync(0xffffffffu, mytau, c);
+        pass |= (__uint_as_float(v[c]) >= t ? 1u : 0u) << c;
     }
     if (!row_ok) pass = 0;
     if (a.dump && row_ok) {
@@ -449,7 +436,7 @@ __device__ __forceinline__ void handle_survivors(const ScanArgs& a, const uint32
 
 // taddr: TMEM address of this warp's first column (lane quadrant included); q0: first query of it.
 // `release` is called exactly once, right after this warp's last read of the accumulator.
-template <int NG, bool TAU_SHFL, typename Release>
+template <int NG, typename Release>
 __device__ __forceinline__ void filter_item(const ScanArgs& a, uint32_t taddr, int64_t q0, int64_t row, bool row_ok,
                                             int lane, Stash& st, const float (&mytau)[NG], Release release) {
     stash_clear(st);
@@ -460,7 +447,7 @@ __device__ __forceinline__ void filter_item(const ScanArgs& a, uint32_t taddr, i
         uint32_t v[32];
         tmem_ld32(taddr + g * 32, v);
         tmem_ld_wait();
-        const uint32_t pass = pass_mask<TAU_SHFL>(a, v, q0 + g * 32, row, row_ok, mytau[g]);
+        const uint32_t pass = pass_mask(a, v, q0 + g * 32, row, row_ok, mytau[g]);
         if (__any_sync(0xffffffffu, pass != 0))
             handle_survivors(a, v, pass, q0 + g * 32, g * 32, (int32_t)row, lane, st);
     }
@@ -623,7 +610,7 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
             mbar_wait(&tmem_full[as], aph, 500 + as);
             tc_fence_after();
             uint64_t* const ebar = &tmem_empty[as];
-            filter_item<NG, true>(a, tmem_base + lane_base + as * BQ + col0, (int64_t)qt * BQ + col0, row, row_ok, lane,
+            filter_item<NG>(a, tmem_base + lane_base + as * BQ + col0, (int64_t)qt * BQ + col0, row, row_ok, lane,
                             cur, mytau, [=]() {
                                 // all of this warp's reads of the accumulator are done
                                 tc_fence_before();
@@ -881,7 +868,7 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
             mbar_wait(&tmem_full[as], aph, 500 + as);
             tc_fence_after();
             const uint32_t ebar = leader_empty[as];
-            filter_item<NG, true>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
+            filter_item<NG>(a, tmem_base + lane_base + as * kPairQ + col0, (int64_t)qt * kPairQ + col0, row, row_ok,
                             lane, cur, mytau, [=]() {
                                 tc_fence_before();
                                 __syncwarp();
