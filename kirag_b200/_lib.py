@@ -12,7 +12,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkirag_b200.so")
+# KIRAG_B200_LIB: load another build of the SAME ABI (same-box A/B of kernel changes); default: the in-tree library
+LIB_PATH = os.environ.get("KIRAG_B200_LIB") or os.path.join(HERE, "libkirag_b200.so")
 
 # constants mirrored from the header
 ABI_VERSION = 5

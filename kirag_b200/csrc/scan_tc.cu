@@ -73,6 +73,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
         }
     }
 }
+// Wait of a whole (converged) warp on one barrier: ONE lane polls, the others park at the warp barrier.  All 32 lanes
+// polling costs 32 shared-memory barrier reads per try_wait; in the HBM-bound single-CTA kernel that traffic sits next
+// to the filter warps' accumulator read-out (same-box A/B, gpurun_out/r3f_ab.log: 6.1 -> 6.5 ms at 8 queries).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int tag, int lane) {
+    if (lane == 0) mbar_wait(bar, parity, tag);
+    __syncwarp();
+}
 // One lane of the (converged) warp.  The producer / MMA / forwarder warps run their loops with ALL lanes on warp-uniform
 // values and only predicate the issuing instructions on this: ptxas then keeps smem addresses, descriptors and
 // barrier addresses in uniform registers.  With a single active thread (`if (lane == 0)`) it cannot prove uniformity
@@ -532,7 +539,7 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
                     pfsrc = a.shadow + (size_t)ptile * ((size_t)a.d * kTileRows * 2);
                 }
                 for (int kc = 0; kc < KC; ++kc) {
-                    mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
+                    mbar_wait_warp(&empty_bar[s], ph ^ 1u, 100 + s, lane);
                     uint8_t* dst = stage_base + (size_t)s * stage_bytes;
                     if (elect_one()) {
                         if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
@@ -550,18 +557,18 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
         // ================================= MMA ==================================
         {
             constexpr uint32_t idesc = make_idesc_bf16(kTileRows, BQ);
-            if (RESIDENT) mbar_wait(q_bar, 0, 200);
+            if (RESIDENT) mbar_wait_warp(q_bar, 0, 200, lane);
             int s = 0;
             uint32_t ph = 0;
             uint32_t it = 0;
             for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
                 const uint32_t as = it & 1u;
                 const uint32_t aph = (it >> 1) & 1u;
-                mbar_wait(&tmem_empty[as], aph ^ 1u, 300 + as);
+                mbar_wait_warp(&tmem_empty[as], aph ^ 1u, 300 + as, lane);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BQ;
                 for (int kc = 0; kc < KC; ++kc) {
-                    mbar_wait(&full_bar[s], ph, 400 + s);
+                    mbar_wait_warp(&full_bar[s], ph, 400 + s, lane);
                     tc_fence_after();
                     const uint32_t xa = smem_u32(stage_base + (size_t)s * stage_bytes);
                     const uint32_t qa = RESIDENT ? smem_u32(q_res + (size_t)kc * kQBlockBytes) : xa + kBlockBytes;
@@ -756,7 +763,7 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
                 // tiles, not live ones, make room for the next tiles
                 const uint64_t pol_xw = (a.x_policy == 3 && n_qt > 1 && qt == n_qt - 1) ? pol_x_last : pol_x;
                 for (int kc = 0; kc < KC; ++kc) {
-                    mbar_wait(&empty_bar[s], ph ^ 1u, 100 + s);
+                    mbar_wait_warp(&empty_bar[s], ph ^ 1u, 100 + s, lane);
                     uint8_t* dst = stage_base + (size_t)s * kPairStageBytes;
                     if (elect_one()) {
                         if (pfsrc) bulk_prefetch_l2(pfsrc + (size_t)kc * kBlockBytes, kBlockBytes);
@@ -782,13 +789,13 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
             if (half == 1) {
                 // ============================= forwarder =============================
                 if (RES) {
-                    mbar_wait(q_bar, 0, 650);                          // this CTA's half of the query tile has landed
+                    mbar_wait_warp(q_bar, 0, 650, lane);                          // this CTA's half of the query tile has landed
                     if (elect_one()) mbar_arrive_cluster(map_to_rank(q_bar, leader));   // tell the leader
                     __syncwarp();
                 }
                 for (int64_t w = w_lo; w < w_hi; ++w) {
                     for (int kc = 0; kc < KC; ++kc) {
-                        mbar_wait(&full_bar[s], ph, 600 + s);               // this CTA's stage has landed
+                        mbar_wait_warp(&full_bar[s], ph, 600 + s, lane);               // this CTA's stage has landed
                         if (elect_one()) mbar_arrive_cluster(map_to_rank(&full_bar[s], leader));  // tell the leader
                         __syncwarp();
                         if (++s == NS) { s = 0; ph ^= 1u; }
@@ -797,16 +804,16 @@ __device__ __forceinline__ void scan_pair_body(const ScanArgs& a) {
             } else {
                 // ================================ MMA ================================
                 constexpr uint32_t idesc = make_idesc_bf16(2 * kTileRows, kPairQ);
-                if (RES) mbar_wait(q_bar, 0, 200);  // both halves of the query tile are resident
+                if (RES) mbar_wait_warp(q_bar, 0, 200, lane);  // both halves of the query tile are resident
                 uint32_t it = 0;
                 for (int64_t w = w_lo; w < w_hi; ++w, ++it) {
                     const uint32_t as = it & 1u;
                     const uint32_t aph = (it >> 1) & 1u;
-                    mbar_wait(&tmem_empty[as], aph ^ 1u, 300 + as);
+                    mbar_wait_warp(&tmem_empty[as], aph ^ 1u, 300 + as, lane);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * kPairQ;
                     for (int kc = 0; kc < KC; ++kc) {
-                        mbar_wait(&full_bar[s], ph, 400 + s);  // own bytes + the peer's forward
+                        mbar_wait_warp(&full_bar[s], ph, 400 + s, lane);  // own bytes + the peer's forward
                         tc_fence_after();
                         const uint32_t xa = smem_u32(stage_base + (size_t)s * kPairStageBytes);
                         const uint64_t da = make_sw128_desc(xa);
