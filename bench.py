@@ -319,7 +319,7 @@ def measure_batch(sh, lib, q_all, batch, k, steps, warmup, device, dist_ok, peak
                  "run (DRAM counters cannot be read from inside a run): read from the committed single-pass ncu capture of the "
                  "same command (profiles/r02_scan_traffic.json, raw list profiles/r02_traffic_b4096.csv)",
                  "kernel": ("scan_tc_pair_kernel<256,streamed>" if batch > 128 else "scan_tc_pair_kernel<128,resident>"
-                            if batch > 64 else "scan_tc_kernel<%d,resident>" % (32 if batch <= 32 else 64)), "kernel_ms_per_step": scan_ms_step,
+                            if batch > 64 else "scan_tc_pair_kernel<64,resident>"), "kernel_ms_per_step": scan_ms_step,
                  "kernel_share_of_step": scan_ms_step / ms if ms > 0 else None,
                  "launches_per_step": launches.value / steps, "peak_source": peaks["source"],
                  "algorithmic_bytes_per_step": bytes_alg, "algorithmic_flops_per_step": flops_alg,

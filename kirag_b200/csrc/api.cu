@@ -1330,7 +1330,7 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
     if (force && *force) {
         // 32 / 64 / 128 / 256: single-CTA kernels (32 resident, the others streamed); 512: the 2-CTA kernel
         // with 256-query tiles (2512 / 4512: two / four pairs per cluster with multicast query blocks); 1128: the
-        // 2-CTA kernel with a resident 128-query tile; 1064: resident 64
+        // 2-CTA kernel with a resident 128-query tile; 1064: resident 64 (single CTA); 2064: resident 64 (2-CTA)
         plan.bq = atoi(force);
         plan.pair = 0;
         plan.multi = 1;
@@ -1340,6 +1340,7 @@ int kirag_index_debug_scores(kirag_index_t* h, const float* q_host, int64_t nq, 
         if (plan.bq == 4512) { plan.bq = 256; plan.pair = 1; plan.multi = 4; }
         if (plan.bq == 1128) { plan.bq = 128; plan.pair = 1; plan.resident = 1; }
         if (plan.bq == 1064) { plan.bq = 64; plan.resident = 1; }
+        if (plan.bq == 2064) { plan.bq = 64; plan.pair = 1; plan.resident = 1; }  // 2-CTA kernel, resident 64-query tile
         plan.q_tile_rows = plan.pair ? plan.bq / 2 : plan.bq;
     }
     const size_t qs_bytes = scan_tc_qshadow_bytes(nq, d, plan);

@@ -970,7 +970,11 @@ int scan_tc_pick(int64_t nq, int d, ScanTcPlan* plan) {
     const int pair_ok = env_flag("KIRAG_SCAN_PAIR", 1) ? 1 : 0;
     plan->pair = 0;
     plan->multi = 1;
-    if (nq <= 32 && pick_stages(32, true, d) >= 4) { plan->bq = 32; plan->resident = 1; }
+    // up to 64 queries: the 2-CTA kernel with a resident 64-query tile (32 queries = 64 KB per CTA, 10 stages).  Same-box
+    // A/B against the single-CTA resident kernels at 21M rows (gpurun_out/r3j_ab.log, r3k_ab.log): 5.85 vs 6.2 ms at
+    // 1-32 queries (7.3 TB/s whole-step), 6.1 vs 6.4 ms at 48, 6.2-6.6 vs 6.6-6.7 ms at 64.  KIRAG_PAIR64=0: single CTA.
+    if (nq <= 64 && pair_ok && env_flag("KIRAG_PAIR64", 1) && pair_stages<64, true>(d) >= 6) { plan->bq = 64; plan->resident = 1; plan->pair = 1; }
+    else if (nq <= 32 && pick_stages(32, true, d) >= 4) { plan->bq = 32; plan->resident = 1; }
     else if (nq <= 64 && pick_stages(64, true, d) >= 4) { plan->bq = 64; plan->resident = 1; }  // 128 KB of queries + >= 4 stages
     else if (nq <= 64) { plan->bq = 64; plan->resident = 0; }
     else if (nq <= 128 && pair_ok && pair_stages<128, true>(d) >= 4) { plan->bq = 128; plan->resident = 1; plan->pair = 1; }
@@ -1075,6 +1079,7 @@ static int launch_scan_args(const ScanArgs& args, const ScanTcPlan& plan, int nu
     if (plan.pair && plan.bq == 256 && !plan.resident && plan.multi == 4) return launch_scan_multi<4>(args, num_sms, st);
     if (plan.pair && plan.bq == 256 && !plan.resident) return launch_scan_pair<256, false>(args, num_sms, st);
     if (plan.pair && plan.bq == 128 && plan.resident) return launch_scan_pair<128, true>(args, num_sms, st);
+    if (plan.pair && plan.bq == 64 && plan.resident) return launch_scan_pair<64, true>(args, num_sms, st);
     if (plan.bq == 32 && plan.resident) return launch_scan_t<32, true>(args, num_sms, st);
     if (plan.bq == 64 && plan.resident) return launch_scan_t<64, true>(args, num_sms, st);
     if (plan.bq == 64 && !plan.resident) return launch_scan_t<64, false>(args, num_sms, st);

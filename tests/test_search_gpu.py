@@ -92,6 +92,40 @@ def test_tcgen05_scores_match_bf16_reference(fa, n, d, nq):
     assert np.max(np.abs(got - ref) / scale) < 2e-6  # fp32 accumulation of exact bf16 products
 
 
+@pytest.mark.parametrize("code,nq", [("32", 5), ("64", 40), ("1064", 40), ("2064", 40), ("2064", 1), ("128", 100),
+                                     ("1128", 100), ("256", 200), ("512", 300)])
+def test_every_scan_kernel_variant_scores_match_bf16_reference(fa, monkeypatch, code, nq):
+    """Every instantiation of the scan kernel, forced through KIRAG_DEBUG_BQ (the default plan only exercises the ones
+    it picks): single-CTA 32 / 64 resident and 64 / 128 / 256 streamed, 2-CTA resident 64 / 128 and streamed 256."""
+    monkeypatch.setenv("KIRAG_DEBUG_BQ", code)
+    rng = np.random.default_rng(int(code) + nq)
+    n, d = 1300, 256
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xq = rng.standard_normal((nq, d)).astype(np.float32)
+    got = build(fa, xb).debug_scores(xq)
+    ref = bf16_round(xb).astype(np.float64) @ bf16_round(xq).astype(np.float64).T
+    scale = np.linalg.norm(xb, axis=1)[:, None] * np.linalg.norm(xq, axis=1)[None, :]
+    assert np.max(np.abs(got - ref) / scale) < 2e-6
+    xi, qi = int_corpus(rng, 700, 128), int_corpus(rng, nq, 128)
+    goti = build(fa, xi).debug_scores(qi)
+    assert np.array_equal(goti, (xi.astype(np.float64) @ qi.astype(np.float64).T).astype(np.float32))
+
+
+@pytest.mark.parametrize("pair64", ["0", "1"])
+def test_small_batches_on_both_resident_kernels(fa, monkeypatch, pair64):
+    """Batches of up to 64 queries through the 2-CTA resident-64 kernel (default) and through the single-CTA resident
+    kernels (KIRAG_PAIR64=0): same exact answer."""
+    monkeypatch.setenv("KIRAG_PAIR64", pair64)
+    rng = np.random.default_rng(77)
+    xb = unit_rows(rng, 60000, 128)
+    ix = build(fa, xb)
+    for nq in (1, 8, 32, 33, 64):
+        xq = unit_rows(rng, nq, 128)
+        D, I, st = ix.search_ex(xq, 10, path=AUTO)
+        assert st["n_fast"] == nq, st
+        assert_topk_parity(D, I, xb, xq, 10, what=f"pair64={pair64} nq={nq} {st}")
+
+
 def test_tcgen05_scores_exact_on_integers(fa):
     rng = np.random.default_rng(0)
     xb, xq = int_corpus(rng, 1500, 128), int_corpus(rng, 17, 128)
