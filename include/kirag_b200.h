@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KIRAG_ABI_VERSION 5
+#define KIRAG_ABI_VERSION 6
 
 /* metric ids; only inner product is implemented, as only inner product is
  * ever constructed by the reference (retrieve.py:112, faiss_index_corpus.py:29) */
@@ -301,6 +301,14 @@ int kirag_pool_normalize_fwd_saved(const void* hidden, const void* mask, float* 
                                    int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
                                    int hidden_dtype, int mask_dtype, int mode, int normalize,
                                    int device, void* stream);
+
+/* Forward that also writes the result in the dtype of the hidden states (out_typed: device [B, H] of hidden_dtype —
+ * what the reference's ops return for bf16 / fp16 hidden states under autocast, base_trainer.py:498-499), in the same
+ * kernel instead of a separate cast.  out (float32) is still written: the backward needs it; pooled_norm may be NULL. */
+int kirag_pool_normalize_typed(const void* hidden, const void* mask, float* out, void* out_typed, float* pooled_norm,
+                               int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
+                               int hidden_dtype, int mask_dtype, int mode, int normalize,
+                               int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KIRAG_B200_LIB") or os.path.join(HERE, "libkirag_b200.so")
 
 # constants mirrored from the header
-ABI_VERSION = 5
+ABI_VERSION = 6
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 PATH_AUTO, PATH_EXACT, PATH_FAST = 0, 1, 2
@@ -97,6 +97,8 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "kirag_pool_normalize_fwd_saved": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                                c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "kirag_pool_normalize_typed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                           c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "kirag_pool_normalize_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                               c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

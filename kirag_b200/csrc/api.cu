@@ -1630,7 +1630,7 @@ int kirag_pool_normalize(const void* hidden, const void* mask, float* out, int64
     KIRAG_CHECK(hidden && out, "pool_normalize: null buffer");
     DeviceGuard guard(device);
     if (!guard.ok) return 1;
-    return launch_pool_normalize(hidden, mask, out, nullptr, B, S, H, sb, ss, mb, hidden_dtype, mask_dtype, mode,
+    return launch_pool_normalize(hidden, mask, out, nullptr, nullptr, B, S, H, sb, ss, mb, hidden_dtype, mask_dtype, mode,
                                  normalize, (cudaStream_t)stream);
 }
 
@@ -1641,7 +1641,18 @@ int kirag_pool_normalize_fwd_saved(const void* hidden, const void* mask, float* 
     KIRAG_CHECK(hidden && out && pooled_norm, "pool_normalize_fwd_saved: null buffer");
     DeviceGuard guard(device);
     if (!guard.ok) return 1;
-    return launch_pool_normalize(hidden, mask, out, pooled_norm, B, S, H, sb, ss, mb, hidden_dtype, mask_dtype,
+    return launch_pool_normalize(hidden, mask, out, nullptr, pooled_norm, B, S, H, sb, ss, mb, hidden_dtype, mask_dtype,
+                                 mode, normalize, (cudaStream_t)stream);
+}
+
+int kirag_pool_normalize_typed(const void* hidden, const void* mask, float* out, void* out_typed, float* pooled_norm,
+                               int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
+                               int hidden_dtype, int mask_dtype, int mode, int normalize, int device,
+                               void* stream) {
+    KIRAG_CHECK(hidden && out && out_typed, "pool_normalize_typed: null buffer");
+    DeviceGuard guard(device);
+    if (!guard.ok) return 1;
+    return launch_pool_normalize(hidden, mask, out, out_typed, pooled_norm, B, S, H, sb, ss, mb, hidden_dtype, mask_dtype,
                                  mode, normalize, (cudaStream_t)stream);
 }
 

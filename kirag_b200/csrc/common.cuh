@@ -252,7 +252,7 @@ int launch_scan_tc_dump(const void* shadow, int64_t n_rows, int d, const void* q
                         const ScanTcPlan& plan, const float* tau_inf, int* cnt_scratch, float* dump,
                         int64_t dump_ld, int num_sms, cudaStream_t st);
 // pool.cu
-int launch_pool_normalize(const void* hidden, const void* mask, float* out, float* pooled_norm,
+int launch_pool_normalize(const void* hidden, const void* mask, float* out, void* out_lp, float* pooled_norm,
                           int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
                           int hidden_dtype, int mask_dtype, int mode, int normalize,
                           cudaStream_t st);

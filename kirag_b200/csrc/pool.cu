@@ -15,6 +15,8 @@
 // HBM-bound.  Algorithmic bytes per launch = sum_b len_b * H * sizeof(hidden)
 // + B*S*sizeof(mask) + B*H*4.
 #include "common.cuh"
+#include <cstdlib>
+#include <cmath>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -140,7 +142,7 @@ constexpr int kPoolMaxAcc = 4;  // TPR <= 1024 chunks per row
 template <typename T, bool VEC, int NACC>
 __global__ void __launch_bounds__(kPoolThreads)
 pool_normalize_kernel(const T* __restrict__ hidden, const void* __restrict__ mask,
-                      float* __restrict__ out, float* __restrict__ pooled_norm, int64_t S, int64_t H,
+                      float* __restrict__ out, T* __restrict__ out_lp, float* __restrict__ pooled_norm, int64_t S, int64_t H,
                       int64_t sb, int64_t ss, int64_t mb, int mask_dtype, int mode, int normalize) {
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks();
@@ -290,9 +292,15 @@ pool_normalize_kernel(const T* __restrict__ hidden, const void* __restrict__ mas
     }
     const float nrm = sqrtf(total_ss);
     if (rank == 0 && tid == 0 && pooled_norm) pooled_norm[b] = nrm;
-    if (normalize) {
-        const float dn = fmaxf(nrm, 1e-12f);
-        for (int64_t c = c_lo + tid; c < c_hi; c += kPoolThreads) out[b * H + c] = out[b * H + c] / dn;
+    if (normalize || out_lp) {
+        // out_lp (optional): the result once more in the dtype of the hidden states — what the reference's ops return
+        // for bf16 / fp16 inputs — written here instead of by a separate cast kernel
+        const float dn = normalize ? fmaxf(nrm, 1e-12f) : 1.0f;
+        for (int64_t c = c_lo + tid; c < c_hi; c += kPoolThreads) {
+            const float v = out[b * H + c] / dn;
+            if (normalize) out[b * H + c] = v;
+            if (out_lp) HiddenLoad<T>::store1(out_lp + b * H + c, v);
+        }
     }
     cluster.sync();  // peers may still be reading this CTA's shared memory
 }
@@ -359,10 +367,35 @@ pool_normalize_backward_kernel(const float* __restrict__ grad_out, const float* 
 }
 
 template <typename T, bool VEC, int NACC>
-static int pool_launch_cfg(const void* hidden, const void* mask, float* out, float* pooled_norm, int64_t B, int64_t S,
+static int pool_launch_cfg(const void* hidden, const void* mask, float* out, void* out_lp, float* pooled_norm, int64_t B, int64_t S,
                            int64_t H, int64_t sb, int64_t ss, int64_t mb, int mask_dtype, int mode, int normalize,
                            int cl, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024 && ensure_dynamic_smem(pool_normalize_kernel<T, VEC, NACC>, smem)) return 1;
+    if (cl == 0) {
+        // Cluster size (CTAs per batch row): of the sizes 1/2/4/8 that give at least 3 CTAs per SM's worth of grid,
+        // the one whose grid fills its last wave best, the smallest on a tie.  Measured (tools/pool_ab.py, full masks,
+        // [B,512,1024]): B=256 2 CTAs per row 85 us fp32 / 50 us bf16 vs 98 / 60 us with 4 (1.38 waves); B=1024 2 CTAs per
+        // row 319 us vs 331 us with 1.
+        static int per_sm_cache = 0;
+        static size_t per_sm_smem = (size_t)-1;
+        if (per_sm_smem != smem) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pool_normalize_kernel<T, VEC, NACC>, kPoolThreads, smem) !=
+                    cudaSuccess || n <= 0) { cudaGetLastError(); n = 4; }
+            per_sm_cache = n;
+            per_sm_smem = smem;
+        }
+        const double slots = 148.0 * per_sm_cache;
+        double best = -1.0;
+        cl = 8;
+        for (int c = 1; c <= 8; c *= 2) {
+            const double ctas = (double)B * c;
+            if (ctas < 148.0 * 3 && c < 8) continue;
+            const double waves = ctas / slots;
+            const double eff = waves <= 1.0 ? 1.0 : waves / ceil(waves);  // one partial wave has no tail
+            if (eff > best + 1e-9) { best = eff; cl = c; }
+        }
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(B * cl));
     cfg.blockDim = dim3(kPoolThreads);
@@ -376,14 +409,14 @@ static int pool_launch_cfg(const void* hidden, const void* mask, float* out, flo
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const T* hp = (const T*)hidden;
-    KIRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, pool_normalize_kernel<T, VEC, NACC>, hp, mask, out, pooled_norm, S, H, sb, ss, mb,
+    KIRAG_CUDA_OK(cudaLaunchKernelEx(&cfg, pool_normalize_kernel<T, VEC, NACC>, hp, mask, out, (T*)out_lp, pooled_norm, S, H, sb, ss, mb,
                                      mask_dtype, mode, normalize));
     count_launch();
     return 0;
 }
 
 template <typename T>
-static int pool_launch_t(const void* hidden, const void* mask, float* out, float* pooled_norm,
+static int pool_launch_t(const void* hidden, const void* mask, float* out, void* out_lp, float* pooled_norm,
                          int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
                          int mask_dtype, int mode, int normalize, cudaStream_t st) {
     constexpr int E = Vec16<T>::kElems;
@@ -397,12 +430,14 @@ static int pool_launch_t(const void* hidden, const void* mask, float* out, float
     const size_t smem = ((((size_t)S + 2 * (size_t)n_words + 1) * 4 + 15) & ~(size_t)15) + (size_t)R * Hpad * 4 + 16 * 4;
     KIRAG_CHECK(smem <= 200 * 1024, "pool_normalize: S=%lld H=%lld need %zu B of shared memory",
                 (long long)S, (long long)H, smem);
-    // cluster size: the smallest of 1/2/4/8 that gives at least 4 CTAs per SM's worth of grid
-    int cl = 8;
-    for (int c = 1; c <= 8; c *= 2) if (B * c >= 148 * 4) { cl = c; break; }
+    int cl = 0;  // 0: chosen per kernel instantiation in pool_launch_cfg (needs its occupancy)
+    {   // experiment knob
+        const char* v = getenv("KIRAG_POOL_CL");
+        if (v && *v) { const int c = atoi(v); if (c == 1 || c == 2 || c == 4 || c == 8) cl = c; }
+    }
     if (mode == 1) cl = 1;  // CLS: one token per row
 #define KIRAG_POOL_GO(VECF, NACC) \
-    pool_launch_cfg<T, VECF, NACC>(hidden, mask, out, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, cl, smem, st)
+    pool_launch_cfg<T, VECF, NACC>(hidden, mask, out, out_lp, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, cl, smem, st)
     if (!vec) return KIRAG_POOL_GO(false, 1);
     const int nacc = tpr >= kPoolThreads ? (int)(tpr / kPoolThreads) : 1;
     if (nacc == 1) return KIRAG_POOL_GO(true, 1);
@@ -412,7 +447,7 @@ static int pool_launch_t(const void* hidden, const void* mask, float* out, float
 #undef KIRAG_POOL_GO
 }
 
-int launch_pool_normalize(const void* hidden, const void* mask, float* out, float* pooled_norm,
+int launch_pool_normalize(const void* hidden, const void* mask, float* out, void* out_lp, float* pooled_norm,
                           int64_t B, int64_t S, int64_t H, int64_t sb, int64_t ss, int64_t mb,
                           int hidden_dtype, int mask_dtype, int mode, int normalize,
                           cudaStream_t st) {
@@ -425,9 +460,9 @@ int launch_pool_normalize(const void* hidden, const void* mask, float* out, floa
     KIRAG_CHECK(mask_dtype >= 0 && mask_dtype <= 2, "pool_normalize: unknown mask dtype %d", mask_dtype);
     KIRAG_CHECK(mode == 1 || mask != nullptr, "pool_normalize: mean mode needs a mask");
     switch (hidden_dtype) {
-        case 0: return pool_launch_t<float>(hidden, mask, out, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, st);
-        case 1: return pool_launch_t<__nv_bfloat16>(hidden, mask, out, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, st);
-        case 2: return pool_launch_t<__half>(hidden, mask, out, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, st);
+        case 0: return pool_launch_t<float>(hidden, mask, out, out_lp, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, st);
+        case 1: return pool_launch_t<__nv_bfloat16>(hidden, mask, out, out_lp, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, st);
+        case 2: return pool_launch_t<__half>(hidden, mask, out, out_lp, pooled_norm, B, S, H, sb, ss, mb, mask_dtype, mode, normalize, st);
         default: break;
     }
     set_error("pool_normalize: unknown hidden dtype %d", hidden_dtype);

@@ -53,27 +53,38 @@ def _prep(hidden: torch.Tensor, mask, mode: int):
 
 class _PoolNormalize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, mask, mode: int, normalize: bool):
+    def forward(ctx, hidden, mask, mode: int, normalize: bool, typed: bool):
         hidden, mask = _prep(hidden, mask, mode)
         B, S, H = hidden.shape
         lib = _lib.load()
         out = torch.empty((B, H), dtype=torch.float32, device=hidden.device)
         norms = torch.empty((B,), dtype=torch.float32, device=hidden.device)
+        # bf16 / fp16 hidden states (autocast): the kernel also writes the result in that dtype — no cast kernel
+        typed = bool(typed) and hidden.dtype != torch.float32
+        out_typed = torch.empty((B, H), dtype=hidden.dtype, device=hidden.device) if typed else None
         st = torch.cuda.current_stream(hidden.device).cuda_stream
         mdt = _MASK_DTYPES[mask.dtype] if mask is not None else _lib.MASK_I64
         mb = mask.stride(0) if mask is not None else 0
         if B > 0:
-            _lib.check(
-                lib.kirag_pool_normalize_fwd_saved(
-                    _p(hidden), _p(mask), _p(out), _p(norms), B, S, H, hidden.stride(0), hidden.stride(1), mb,
-                    _HIDDEN_DTYPES[hidden.dtype], mdt, mode, int(bool(normalize)), hidden.device.index,
-                    ctypes.c_void_p(st)),
-                "pool_normalize")
+            if typed:
+                _lib.check(
+                    lib.kirag_pool_normalize_typed(
+                        _p(hidden), _p(mask), _p(out), _p(out_typed), _p(norms), B, S, H, hidden.stride(0),
+                        hidden.stride(1), mb, _HIDDEN_DTYPES[hidden.dtype], mdt, mode, int(bool(normalize)),
+                        hidden.device.index, ctypes.c_void_p(st)),
+                    "pool_normalize_typed")
+            else:
+                _lib.check(
+                    lib.kirag_pool_normalize_fwd_saved(
+                        _p(hidden), _p(mask), _p(out), _p(norms), B, S, H, hidden.stride(0), hidden.stride(1), mb,
+                        _HIDDEN_DTYPES[hidden.dtype], mdt, mode, int(bool(normalize)), hidden.device.index,
+                        ctypes.c_void_p(st)),
+                    "pool_normalize")
         ctx.mode, ctx.normalize = mode, bool(normalize)
         ctx.hidden_dtype, ctx.shape = hidden.dtype, (B, S, H)
         ctx.save_for_backward(out, norms, mask if mask is not None else torch.empty(0, device=hidden.device))
         ctx.has_mask = mask is not None
-        return out
+        return out_typed if typed else out
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -93,7 +104,7 @@ class _PoolNormalize(torch.autograd.Function):
                     _HIDDEN_DTYPES[ctx.hidden_dtype], mdt, ctx.mode, int(ctx.normalize), grad_out.device.index,
                     ctypes.c_void_p(st)),
                 "pool_normalize_backward")
-        return grad_hidden, None, None, None
+        return grad_hidden, None, None, None, None
 
 
 def pool_normalize(last_hidden_states: torch.Tensor, attention_mask=None, mode: str = "mean",
@@ -101,8 +112,8 @@ def pool_normalize(last_hidden_states: torch.Tensor, attention_mask=None, mode: 
     """Fused epilogue.  mode 'mean' (E5) or 'cls' (BGE).  Returns [B, H]; dtype follows the
     hidden states (as the reference's ops do) unless out_dtype is given."""
     m = {"mean": _lib.POOL_MEAN, "cls": _lib.POOL_CLS}[mode]
-    out = _PoolNormalize.apply(last_hidden_states, attention_mask, m, normalize)
     want = last_hidden_states.dtype if out_dtype is None else out_dtype
+    out = _PoolNormalize.apply(last_hidden_states, attention_mask, m, normalize, want == last_hidden_states.dtype)
     return out if out.dtype == want else out.to(want)
 
 
