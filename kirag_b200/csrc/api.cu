@@ -1140,14 +1140,6 @@ int kirag_index_create(int d, int metric, int device, kirag_index_t** out) {
     h->metric = metric;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
-    {   // experiment knob: L2 set-aside for persisting (evict_last) accesses, in MB (default: leave the driver's setting)
-        const int mb = env_int("KIRAG_L2_PERSIST_MB", -1);
-        if (mb >= 0) {
-            size_t want = (size_t)mb << 20;
-            if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
-        }
-    }
     if (cudaMalloc((void**)&h->maxnorm2_bits, 12) != cudaSuccess || cudaMemset(h->maxnorm2_bits, 0, 12) != cudaSuccess) {
         set_error("index_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete h;
