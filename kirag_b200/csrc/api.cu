@@ -1434,22 +1434,46 @@ int kirag_index_save(const kirag_index_t* h, const char* path) {
     ok = ok && fwrite(&fourcc, 4, 1, f) == 1 && fwrite(&d, 4, 1, f) == 1 && fwrite(&ntotal, 8, 1, f) == 1 &&
          fwrite(&dummy, 8, 1, f) == 1 && fwrite(&dummy, 8, 1, f) == 1 && fwrite(&trained, 1, 1, f) == 1 &&
          fwrite(&metric, 4, 1, f) == 1 && fwrite(&words, 8, 1, f) == 1;
-    float* stage = nullptr;
+    // two pinned buffers: the device -> host copy of piece i+1 runs while piece i is being written
+    float* stage[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
     const size_t chunk_bytes = kIoChunkRows * (size_t)d * 4;
-    if (ok && ntotal > 0 && cudaMallocHost((void**)&stage, chunk_bytes) != cudaSuccess) {
-        set_error("index_save: cudaMallocHost failed");
-        fclose(f);
-        return 1;
-    }
-    for (int64_t r = 0; ok && r < ntotal; r += (int64_t)kIoChunkRows) {
-        const int64_t rows = (ntotal - r < (int64_t)kIoChunkRows) ? (ntotal - r) : (int64_t)kIoChunkRows;
-        if (cudaMemcpy(stage, h->master + r * d, (size_t)rows * d * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (ok && ntotal > 0) {
+        bool alloc_ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2; ++i)
+            alloc_ok = alloc_ok && cudaMallocHost((void**)&stage[i], chunk_bytes) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!alloc_ok) {
+            set_error("index_save: pinned staging buffers: %s", cudaGetErrorString(cudaGetLastError()));
             ok = false;
-            break;
         }
-        ok = fwrite(stage, 4, (size_t)rows * d, f) == (size_t)rows * d;
     }
-    if (stage) cudaFreeHost(stage);
+    const int64_t n_pieces = (ntotal + (int64_t)kIoChunkRows - 1) / (int64_t)kIoChunkRows;
+    auto piece_rows = [&](int64_t i) {
+        const int64_t r = i * (int64_t)kIoChunkRows;
+        return (ntotal - r < (int64_t)kIoChunkRows) ? (ntotal - r) : (int64_t)kIoChunkRows;
+    };
+    auto enqueue = [&](int64_t i) {
+        const int b = (int)(i & 1);
+        return cudaMemcpyAsync(stage[b], h->master + i * (int64_t)kIoChunkRows * d, (size_t)piece_rows(i) * d * 4,
+                               cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+               cudaEventRecord(copied[b], st) == cudaSuccess;
+    };
+    if (ok && n_pieces > 0) ok = enqueue(0);
+    for (int64_t i = 0; ok && i < n_pieces; ++i) {
+        const int b = (int)(i & 1);
+        if (cudaEventSynchronize(copied[b]) != cudaSuccess) { ok = false; break; }
+        if (i + 1 < n_pieces && !enqueue(i + 1)) { ok = false; break; }  // the other buffer was written out last round
+        const size_t n_el = (size_t)piece_rows(i) * d;
+        ok = fwrite(stage[b], 4, n_el, f) == n_el;
+    }
+    if (st) cudaStreamSynchronize(st);
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+    }
+    if (st) cudaStreamDestroy(st);
     if (fclose(f) != 0) ok = false;
     KIRAG_CHECK(ok, "index_save: write to %s failed", path);
     return 0;
