@@ -321,7 +321,7 @@ struct kirag_index {
     bool center_decided = false;
     // workspaces (grow-only)
     DevBuf q_dev, D_dev, I_dev, qshadow, qnorm, cand, cnt, tau, tauk, overflow, flags, rescored;
-    DevBuf dense, stage_a, stage_b, qmap, qsel, qnorm2, D_tmp, I_tmp;
+    DevBuf dense, stage_a, stage_b, qmap, qsel, qnorm2, D_tmp, I_tmp, t_dev, center_sums;
     int* host_flags = nullptr;  // pinned: certificate read-back without a staging copy
     size_t host_flags_n = 0;
     PendingSearch pending;
@@ -344,12 +344,14 @@ static int env_int(const char* name, int dflt) {
 // cosine 0.7+) get c ~ their common direction.  Any fixed c is valid — it shifts all scores of a query by <q, c> — so
 // rows added later need not share the mean for exactness, only for the certificate to stay tight.
 constexpr int64_t kCenterMinRows = 4096;
-constexpr int64_t kCenterSampleRows = 65536;
+// E||mean||^2 of n i.i.d. unit rows is 1/n, so 8192 rows decide safely, and a centre that is 1 % off costs the
+// certificate nothing; summing 65536 rows took 50 us of every transient kirag_topk_ip index.
+constexpr int64_t kCenterSampleRows = 8192;
 static int decide_center(kirag_index* h, int64_t rows_available, cudaStream_t st) {
     if (env_int("KIRAG_NO_CENTER", 0)) return 0;
     const int d = h->d;
     const int64_t rows = rows_available < kCenterSampleRows ? rows_available : kCenterSampleRows;
-    DevBuf sums;
+    DevBuf& sums = h->center_sums;  // kept: a cudaMalloc / cudaFree pair per transient index (kirag_topk_ip) cost ~60 us
     if (sums.ensure((size_t)(d + 1) * 4)) return 1;
     std::vector<float> host((size_t)d + 1);
     int rc = 1;
@@ -383,7 +385,6 @@ static int decide_center(kirag_index* h, int64_t rows_available, cudaStream_t st
         h->center_norm = (float)sqrt(c2);
         rc = 0;
     } while (0);
-    sums.release();
     return rc;
 }
 
@@ -1163,7 +1164,7 @@ int kirag_index_destroy(kirag_index_t* h) {
     if (h->maxnorm2_bits) cudaFree(h->maxnorm2_bits);
     if (h->center) cudaFree(h->center);
     DevBuf* bufs[] = {&h->q_dev, &h->D_dev, &h->I_dev, &h->qshadow, &h->qnorm, &h->cand, &h->cnt, &h->tau, &h->tauk,
-                      &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel, &h->qnorm2,
+                      &h->overflow, &h->flags, &h->rescored, &h->dense, &h->stage_a, &h->stage_b, &h->qmap, &h->qsel, &h->qnorm2, &h->t_dev, &h->center_sums,
                       &h->D_tmp, &h->I_tmp};
     for (DevBuf* b : bufs) b->release();
     if (h->host_flags) cudaFreeHost(h->host_flags);
@@ -1621,6 +1622,39 @@ int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d,
     if (!guard.ok) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (finish_pending(h, nullptr, nullptr)) return 1;
+    // KiRAG's own shape (models.py:1514-1542: 1-2 chain queries against the 10^2-10^3 triples of the accumulated
+    // documents): building a transient index (copy, bf16 shadow, norm read-back = two host synchronisations) costs far
+    // more than the contraction.  The fp32 scan + select run directly on the caller's matrix instead: three
+    // stream-ordered launches per four queries, the same canonical scores and (score desc, id asc) order.
+    if (nq > 0 && nq <= 2 * kExactNQ && nt > 0 && nt <= 65536) {
+        KIRAG_CHECK(q && t && D && I, "topk_ip: null buffer");
+        KIRAG_CHECK(k > 0 && k <= 2048, "topk_ip: k=%d not in [1, 2048]", k);
+        const float* qd = q;
+        const float* td = t;
+        float* Dd = D;
+        int64_t* Id = I;
+        if (!ptrs_are_device) {
+            if (h->t_dev.ensure((size_t)nt * d * 4) || h->q_dev.ensure((size_t)nq * d * 4) ||
+                h->D_dev.ensure((size_t)nq * k * 4) || h->I_dev.ensure((size_t)nq * k * 8)) return 1;
+            KIRAG_CUDA_OK(cudaMemcpyAsync(h->t_dev.p, t, (size_t)nt * d * 4, cudaMemcpyHostToDevice, st));
+            KIRAG_CUDA_OK(cudaMemcpyAsync(h->q_dev.p, q, (size_t)nq * d * 4, cudaMemcpyHostToDevice, st));
+            qd = h->q_dev.as<float>(); td = h->t_dev.as<float>(); Dd = h->D_dev.as<float>(); Id = h->I_dev.as<int64_t>();
+        }
+        float* const own_master = h->master;
+        const int64_t own_n = h->ntotal;
+        h->master = const_cast<float*>(td);  // borrowed for the launches below only
+        h->ntotal = nt;
+        const int rc_small = exact_search(h, qd, nq, k, Dd, Id, 0, nullptr, 0, st);
+        h->master = own_master;
+        h->ntotal = own_n;
+        if (rc_small) return 1;
+        if (!ptrs_are_device) {
+            KIRAG_CUDA_OK(cudaMemcpyAsync(D, Dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+            KIRAG_CUDA_OK(cudaMemcpyAsync(I, Id, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+            KIRAG_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        return 0;
+    }
     // forget the previous call's rows (capacity and workspaces stay)
     h->ntotal = 0;
     h->maxnorm = h->maxerr = h->maxnorm_x = h->center_norm = 0.f;

@@ -110,7 +110,14 @@ column_sums_kernel(const float* __restrict__ src, int64_t n_rows, int d, int row
     float sq = 0.0f;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
         float acc = 0.0f;
-        for (int64_t r = r0; r < r1; ++r) {
+        int64_t r = r0;
+        for (; r + 4 <= r1; r += 4) {  // four independent loads in flight
+            const float v0 = src[r * (int64_t)d + c], v1 = src[(r + 1) * (int64_t)d + c];
+            const float v2 = src[(r + 2) * (int64_t)d + c], v3 = src[(r + 3) * (int64_t)d + c];
+            acc += (v0 + v1) + (v2 + v3);
+            sq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, sq))));
+        }
+        for (; r < r1; ++r) {
             const float v = src[r * (int64_t)d + c];
             acc += v;
             sq = fmaf(v, v, sq);
@@ -145,7 +152,7 @@ row_norms_kernel(const float* __restrict__ src, int64_t n_rows, int d,
 
 int launch_column_sums(const float* src, int64_t n_rows, int d, float* sums, cudaStream_t st) {
     if (n_rows <= 0) return 0;
-    const int rows_per_block = 64;
+    const int rows_per_block = 16;  // 512 blocks for the 8192-row sample of the centre decision
     column_sums_kernel<<<(unsigned)((n_rows + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(src, n_rows, d,
                                                                                                     rows_per_block, sums);
     KIRAG_LAUNCH_OK("column_sums_kernel");

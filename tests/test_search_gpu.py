@@ -368,6 +368,30 @@ def test_aligner_scoring_matches_reference_torch_golden(fa):
             assert set(idx[r]) == set(ref_i[r].tolist())
 
 
+@pytest.mark.parametrize("C,T,d,k", [(1, 137, 1024, 20), (2, 900, 1024, 20), (8, 5000, 256, 7), (2, 12, 64, 20),
+                                     (3, 40000, 128, 50)])
+def test_aligner_real_shape_runs_on_the_callers_matrix(fa, C, T, d, k):
+    """KiRAG's own aligner shape (1-2 chain queries x 10^2-10^3 triples, models.py:1514-1542): kirag_topk_ip scans the
+    caller's matrix in place (no transient index) — same canonical scores and order as the index path, from host and
+    from device buffers, ties by lower index, k > T clipped by the Python surface."""
+    import torch
+
+    from kirag_b200.scoring import topk_inner_product
+
+    rng = np.random.default_rng(C * 1000 + T)
+    t, q = unit_rows(rng, T, d), unit_rows(rng, C, d)
+    t[T // 2] = t[T // 3]  # an exact tie
+    D, I = topk_inner_product(q, t, k)
+    kk = min(k, T)
+    assert D.shape == (C, kk) and I.shape == (C, kk)
+    assert_topk_parity(D, I, t, q, kk, what=f"aligner {C}x{T}")
+    Dd, Id = topk_inner_product(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), k)
+    assert np.array_equal(Id.cpu().numpy(), I) and np.array_equal(Dd.cpu().numpy(), D)
+    ix = build(fa, t)  # the index path gives bit-identical scores
+    Di, Ii, _ = ix.search_ex(q, kk, path=EXACT)
+    assert np.array_equal(Ii, I) and np.array_equal(Di, D)
+
+
 def test_config4_aligner_shape(fa):
     """BASELINE configs[4]: 256 chain queries x 50k candidate triples, top-20."""
     rng = np.random.default_rng(14)
