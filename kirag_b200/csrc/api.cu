@@ -1626,7 +1626,9 @@ int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d,
     // documents): building a transient index (copy, bf16 shadow, norm read-back = two host synchronisations) costs far
     // more than the contraction.  The fp32 scan + select run directly on the caller's matrix instead: three
     // stream-ordered launches per four queries, the same canonical scores and (score desc, id asc) order.
-    if (nq > 0 && nq <= 2 * kExactNQ && nt > 0 && nt <= 65536) {
+    // (measured, tools/aligner_latency.py: 2 x 1000 78 us here; above one select segment of 8192 rows the transient
+    // index wins — 8 x 20000: 439 us in place, 16 x 20000 through the index 233 us)
+    if (nq > 0 && nq <= 2 * kExactNQ && nt > 0 && nt <= kSelectSeg) {
         KIRAG_CHECK(q && t && D && I, "topk_ip: null buffer");
         KIRAG_CHECK(k > 0 && k <= 2048, "topk_ip: k=%d not in [1, 2048]", k);
         const float* qd = q;

@@ -369,7 +369,7 @@ def test_aligner_scoring_matches_reference_torch_golden(fa):
 
 
 @pytest.mark.parametrize("C,T,d,k", [(1, 137, 1024, 20), (2, 900, 1024, 20), (8, 5000, 256, 7), (2, 12, 64, 20),
-                                     (3, 40000, 128, 50)])
+                                     (3, 8192, 128, 50), (3, 8193, 128, 50)])
 def test_aligner_real_shape_runs_on_the_callers_matrix(fa, C, T, d, k):
     """KiRAG's own aligner shape (1-2 chain queries x 10^2-10^3 triples, models.py:1514-1542): kirag_topk_ip scans the
     caller's matrix in place (no transient index) — same canonical scores and order as the index path, from host and
