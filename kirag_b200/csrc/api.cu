@@ -1664,6 +1664,17 @@ int kirag_topk_ip(const float* q, int64_t nq, const float* t, int64_t nt, int d,
     if (h->center) { cudaFree(h->center); h->center = nullptr; }
     KIRAG_CUDA_OK(cudaMemsetAsync(h->maxnorm2_bits, 0, 12, st));
     int rc = 0;
+    if (nt > 0 && ptrs_are_device && (reinterpret_cast<uintptr_t>(t) & 15) == 0) {
+        // device-resident candidates: the caller's matrix IS the fp32 master for the duration of this (synchronous)
+        // call — no 4*nt*d-byte copy; only the bf16 shadow and the norm maxima are built in the scratch handle
+        if (index_grow(h, nt, st)) return 1;
+        float* const own_master = h->master;
+        h->master = const_cast<float*>(t);
+        rc = finalize_rows(h, 0, nt, st);
+        if (!rc) rc = kirag_index_search(h, q, nq, k, D, I, ptrs_are_device, 0, stream);
+        h->master = own_master;
+        return rc;
+    }
     if (nt > 0) rc = kirag_index_add(h, t, nt, ptrs_are_device, stream);
     if (!rc) rc = kirag_index_search(h, q, nq, k, D, I, ptrs_are_device, 0, stream);
     return rc;
