@@ -65,3 +65,47 @@ def test_sharded_single_process_equals_unsharded():
             Ds.append(Dr), Is.append(Ir)
         Dm, Im = merge_topk_device(torch.stack(Ds), torch.stack(Is))
         assert np.array_equal(Im.cpu().numpy(), I) and np.array_equal(Dm.cpu().numpy(), D)
+
+
+def test_weighted_shards_single_process_equal_unsharded_and_probe_runs():
+    """Speed-weighted row ranges (ShardedFlatIP(weights=...)): uneven shards, same global answer; the rank-speed probe
+    (measure_rank_weights) runs on one GPU and returns [1.0] without a process group."""
+    from kirag_b200 import faiss_api
+    from kirag_b200.sharded import measure_rank_weights, merge_topk_device, shard_range
+
+    rng = np.random.default_rng(3)
+    n, d, k = 40000, 128, 20
+    xb, xq = int_corpus(rng, n, d), int_corpus(rng, 5, d)
+    full = faiss_api.IndexFlatIP(d)
+    full.add(xb)
+    D, I = full.search(xq, k)
+    q = torch.from_numpy(xq).cuda()
+    w = [1.3, 0.7, 1.05, 0.95]
+    Ds, Is, sizes = [], [], []
+    for r in range(4):
+        lo, hi = shard_range(n, 4, r, w)
+        sizes.append(hi - lo)
+        sh = faiss_api.IndexFlatIP(d)
+        sh.add(xb[lo:hi])
+        Dr, Ir = sh.search_device(q, k, id_offset=lo)
+        Ds.append(Dr), Is.append(Ir)
+    assert sum(sizes) == n and sizes[0] > sizes[2] > sizes[3] > sizes[1]
+    Dm, Im = merge_topk_device(torch.stack(Ds), torch.stack(Is))
+    assert np.array_equal(Im.cpu().numpy(), I) and np.array_equal(Dm.cpu().numpy(), D)
+    assert measure_rank_weights(128, 0, nq=64, k=10, rows=1 << 16, seconds=0.2) == [1.0]
+
+
+def test_search_graph_without_peers_is_the_plain_search():
+    """ShardedFlatIP.search_graph falls back to search() when there is no peer exchange (world size 1)."""
+    from kirag_b200.sharded import ShardedFlatIP
+
+    rng = np.random.default_rng(4)
+    xb, xq = int_corpus(rng, 20000, 128), int_corpus(rng, 3, 128)
+    sh = ShardedFlatIP(128, 20000, rank=0, world_size=1, device=0)
+    sh.add_shard(torch.from_numpy(xb).cuda())
+    q = torch.from_numpy(xq).cuda()
+    D, I = sh.search(q, 10)
+    Dg, Ig = sh.search_graph(q, 10)
+    assert torch.equal(D, Dg) and torch.equal(I, Ig)
+    Do, Io = oracle.flat_ip_search(xb, xq, 10)
+    assert np.array_equal(I.cpu().numpy(), Io)
