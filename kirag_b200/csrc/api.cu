@@ -10,10 +10,14 @@
 //   2. geometric levels over the (permuted) 128-row shadow tiles:
 //        tcgen05 filter scan  -> append (approx score, row) with score >= tau[q]
 //        select               -> keep the k' best, tighten tau[q]
-//   3. rescore the k' survivors from the fp32 master (canonical order)
+//   3. rescore the survivors that can still reach the top-k from the fp32 master (canonical order)
 //   4. final sort by (score desc, id asc), write D/I, evaluate the certificate
-//   5. queries whose certificate failed (or whose buffer overflowed) are
-//      re-answered by the exact fp32 scan.
+//      (3 + 4 + the last select are ONE cluster kernel for calls of at most 128 queries)
+//   5. queries whose buffer overflowed are re-run with a gentle level schedule, queries whose
+//      certificate failed get one more bf16 pass with the provable threshold, whatever is left the
+//      exact fp32 scan (resolve_chunk).
+// Steps 1-4 never synchronise with the host (kirag_index_search_async, CUDA-graph capturable);
+// step 5 follows the one synchronisation that reads the per-query flags.
 #include "common.cuh"
 #include "../../include/kirag_b200.h"
 

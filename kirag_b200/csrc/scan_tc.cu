@@ -7,7 +7,7 @@
 // "does this score enter the running top-k'" test is fused into the
 // accumulator read-out, so the score matrix never exists in memory.
 //
-// Data flow per CTA (persistent, one CTA per SM, 192 threads):
+// Data flow per CTA of the single-CTA kernel (persistent, one CTA per SM):
 //   warp 0   producer : cp.async.bulk (TMA engine, SASS UBLKCP) of 16 KB shadow
 //                       blocks [128 corpus rows x 64 k] into an N-stage ring;
 //                       blocks are stored in HBM as the exact SWIZZLE_128B
@@ -17,10 +17,20 @@
 //                       x N=BQ (queries) x K=16, bf16 in, fp32 accumulate in
 //                       TMEM; two accumulator stages so the read-out of tile t
 //                       overlaps the MMAs of tile t+1
-//   warps 2-5 filter  : tcgen05.ld 32x32b -> thread = one corpus row, registers
-//                       = scores against 32 queries; compare with tau[q];
-//                       survivors are appended to the per-query candidate
-//                       buffer (warp-aggregated atomics, rare after level 0)
+//   warps 2+  filter  : tcgen05.ld 32x32b -> thread = one corpus row, registers
+//                       = scores against 32 queries; compare with tau[q] (held in
+//                       registers, fetched one work item ahead); survivors are
+//                       appended to the per-query candidate buffer
+// Warps 0 and 1 run their loops with all 32 lanes on warp-uniform values and predicate
+// only the issuing instructions on elect.sync (see elect_one); one lane polls the mbarriers.
+//
+// The kernels the plan actually picks (scan_tc_pick) are the 2-CTA ones further down
+// (scan_tc_pair_kernel, cta_group::2: one M=256 MMA per K-step for an SM pair, each CTA
+// stages its own corpus tile and half of the query operand):
+//   <= 64 queries   resident 64-query tile (32 queries = 64 KB per CTA, 10-stage ring)   HBM-bound
+//   <= 128 queries  resident 128-query tile (64 queries = 128 KB per CTA, 6-stage ring)  HBM-bound
+//   larger          streamed 256-query tiles (16 KB corpus + 16 KB query half per stage)  tensor-bound
+// The single-CTA kernel remains for KIRAG_SCAN_PAIR=0 / KIRAG_PAIR64=0 and the forced-variant tests.
 //
 // Roofline: HBM for small query batches (algorithmic bytes = rows * d * 2 per
 // launch, streamed exactly once), tensor pipe for large ones (2 * rows * nq * d
