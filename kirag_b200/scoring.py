@@ -31,6 +31,11 @@ def topk_inner_product(queries, triples, k: int):
 
         q = queries.contiguous().float()
         t = triples.to(q.device).contiguous().float()
+        # the kernels use 16-byte loads: a view whose storage offset breaks that alignment is copied
+        if q.data_ptr() % 16:
+            q = q.clone()
+        if t.data_ptr() % 16:
+            t = t.clone()
         C, d = q.shape
         T = t.shape[0]
         kk = min(int(k), T)

@@ -392,6 +392,26 @@ def test_aligner_real_shape_runs_on_the_callers_matrix(fa, C, T, d, k):
     assert np.array_equal(Ii, I) and np.array_equal(Di, D)
 
 
+def test_aligner_scoring_accepts_unaligned_device_views(fa):
+    """Views with a storage offset that is not a multiple of 16 bytes: copied, not faulted on."""
+    import torch
+
+    from kirag_b200.scoring import topk_inner_product
+
+    rng = np.random.default_rng(91)
+    t, q = unit_rows(rng, 20000, 64), unit_rows(rng, 3, 64)
+    tb = torch.zeros(20000 * 64 + 1, dtype=torch.float32, device="cuda")
+    qb = torch.zeros(3 * 64 + 3, dtype=torch.float32, device="cuda")
+    tv, qv = tb[1:].view(20000, 64), qb[3:].view(3, 64)
+    tv.copy_(torch.from_numpy(t))
+    qv.copy_(torch.from_numpy(q))
+    assert tv.data_ptr() % 16 != 0 and qv.data_ptr() % 16 != 0
+    D, I = topk_inner_product(qv, tv, 20)
+    assert_topk_parity(D.cpu().numpy(), I.cpu().numpy(), t, q, 20, what="unaligned views")
+    D2, I2 = topk_inner_product(qv, tv[:500], 20)  # the in-place small-shape path
+    assert_topk_parity(D2.cpu().numpy(), I2.cpu().numpy(), t[:500], q, 20, what="unaligned views, in place")
+
+
 def test_config4_aligner_shape(fa):
     """BASELINE configs[4]: 256 chain queries x 50k candidate triples, top-20."""
     rng = np.random.default_rng(14)
