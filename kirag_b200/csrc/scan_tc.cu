@@ -660,11 +660,13 @@ __global__ void __launch_bounds__(EpiCfg<BQ>::kThreads, 1) scan_tc_kernel(const 
 // Barriers: full[s] lives in each CTA (leader: own expect_tx + the peer's forwarded arrive);
 // empty[s] and tmem_full[a] are signalled in both CTAs by a multicast tcgen05.commit;
 // tmem_empty[a] of the LEADER collects the 8 filter warps of both CTAs.
-// Two instantiations:
+// Three instantiations:
 //   PQ = 256, streamed  : large batches (tensor-bound); corpus block + half query block per stage
 //   PQ = 128, RES       : 64 < batch <= 128 (HBM-bound); each CTA keeps ITS half of the single query
 //                         tile (64 queries x d, 128 KB at d = 1024) resident in shared memory, so
 //                         only corpus blocks are streamed: L2 -> SM traffic equals the HBM traffic
+//   PQ = 64, RES        : batch <= 64 (HBM-bound, the default for KiRAG's 1-2 queries per retrieval):
+//                         32 queries = 64 KB resident per CTA, 10-stage ring, four filter warps
 template <int PQ, bool RES> struct PairCfg {
     static constexpr int kHalfQ = PQ / 2;                      // query rows staged per CTA
     static constexpr int kQHalfBytes = kHalfQ * 128;           // one [half x 64] bf16 block
@@ -675,7 +677,8 @@ template <int PQ, bool RES> struct PairCfg {
 // of a cluster work on different corpus tiles but on the SAME query tile and k-block at the same time, and the
 // 16 KB query half-block that the "same half" CTAs of all pairs need is fetched from L2 ONCE and multicast to them
 // (cp.async.bulk ... .multicast::cluster).  The streamed kernel is bound by the L2 -> SM fill path (32 KB per CTA
-// per 512 tensor cycles: the pipe is 84-85 % active with operands that all hit L2, ncu r01b / r2a), and half of
+// per 512 tensor cycles: the pipe was 84-85 % active with operands that all hit L2, ncu r01b / r2a — before the
+// warp-uniform issue loops, which turned out to be the actual cause; measured again after them: still slower), and half of
 // that traffic is the query operand; with NP pairs sharing it the fill drops to 16 + 16/NP KB per CTA and k-block.
 //   pair j's CTAs issue the query blocks of the k-blocks kc with kc % NP == j, for every pair;
 //   a stage may be refilled only when EVERY pair has consumed it: empty[s] collects one tcgen05.commit per pair
