@@ -561,7 +561,7 @@ static std::vector<int64_t> level_bounds(int64_t n_tiles, int cap, const FastPar
     // growth of level 1: 4; 16 for calls of at most kFewQueries queries (KiRAG's own shape: 1-2 queries per
     // retrieval), where one level less is worth ~35 us per call on a 2.6M-row shard (0.92 -> 0.88 ms).  With 32 or
     // more queries the 4x more survivors of a 16x level cost more than the level saves (measured: 0.92 -> 0.95 ms
-    // at 32 queries, gpurun_out/r2f_knobs.log).  An overflow is re-answered with the gentle schedule.
+    // at 32 queries, profiles/r02_ab/r2f_knobs.log).  An overflow is re-answered with the gentle schedule.
     int g1 = (cap >= kWideCap && fp.few_queries) ? 16 : 4;
     if (fp.first_growth_override > 0) g1 = fp.first_growth_override;
     if (g1 > gmax) g1 = gmax;

@@ -85,7 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 }
 // Wait of a whole (converged) warp on one barrier: ONE lane polls, the others park at the warp barrier.  All 32 lanes
 // polling costs 32 shared-memory barrier reads per try_wait; in the HBM-bound single-CTA kernel that traffic sits next
-// to the filter warps' accumulator read-out (same-box A/B, gpurun_out/r3f_ab.log: 6.1 -> 6.5 ms at 8 queries).
+// to the filter warps' accumulator read-out (same-box A/B, profiles/r02_ab/r3f_ab.log: 6.1 -> 6.5 ms at 8 queries).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int tag, int lane) {
     if (lane == 0) mbar_wait(bar, parity, tag);
     __syncwarp();
@@ -131,7 +131,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 // Pull a block into L2 ahead of the shared-memory ring (KIRAG_PF_TILES > 0).  Hypothesis tested in round 2: at the
 // ridge (B ~ 256) the ring (7 x 16 KB of corpus per SM) bounds the HBM bytes in flight (ncu r2a: DRAM 52 %, tensor
-// 57 %), and a prefetch needs no shared-memory slot.  Measured at 21M rows (gpurun_out/r2c_knobs.log): SLOWER at every
+// 57 %), and a prefetch needs no shared-memory slot.  Measured at 21M rows (profiles/r02_ab/r2c_knobs.log): SLOWER at every
 // batch size (B=256 14.6-14.9 vs 12.2-13.4 ms; the extra bulk requests load the same TMA / L2 path), so it is off.
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
@@ -411,7 +411,7 @@ __device__ __forceinline__ void handle_survivors(const ScanArgs& a, const uint32
         // the common case after the first levels: a binary select tree over the 32 registers (31 SEL per survivor,
         // no memory).  The per-thread scratch below cost 4 KB of local stores per warp and call: 14 GB of L2 writes
         // per 2.6M-row level at 4096 queries, 10 % of the kernel's L2 sectors (ncu r2m), 2.9 GB of DRAM write-backs
-        // per 21M-row step.  Same-process A/B (gpurun_out/r2q, r2r): 21M rows B=4096 137.5 -> 135.4 ms, B=256
+        // per 21M-row step.  Same-process A/B (profiles/r02_ab/r2q, r2r): 21M rows B=4096 137.5 -> 135.4 ms, B=256
         // 10.9 -> 9.4 ms, 2.6M rows B=128 1.07 -> 1.02 ms, B <= 64 unchanged.
         for (uint32_t u = pass; u; u &= u - 1) {
             const int c = __ffs(u) - 1;
@@ -952,7 +952,7 @@ static int env_flag(const char* name, int dflt) {
 // Grid of a scan launch: one CTA (pair) per SM (pair) with equal contiguous work ranges.  ncu (r2a, B = 256)
 // shows sm__cycles_active between 0.99M and 1.43M of 1.44M elapsed cycles, which suggested cutting long levels
 // into more CTAs than SMs so that the hardware block scheduler balances them (KIRAG_SCAN_WAVES > 1: up to that
-// many ranges per SM, none shorter than `min_items` work items).  Measured at 21M rows (gpurun_out/r2c_knobs.log):
+// many ranges per SM, none shorter than `min_items` work items).  Measured at 21M rows (profiles/r02_ab/r2c_knobs.log):
 // no gain at any batch size (B=256 13.3 vs 13.4 ms, B=512 20.5 vs 19.2 ms), so the default stays 1.
 constexpr int64_t kWaveItems = 48;  // corpus tiles (or tile pairs) per range, times the number of query tiles
 static int64_t scan_grid_limit(int64_t work_items, int64_t slots, int64_t min_items) {
@@ -984,7 +984,7 @@ int scan_tc_pick(int64_t nq, int d, ScanTcPlan* plan) {
     plan->pair = 0;
     plan->multi = 1;
     // up to 64 queries: the 2-CTA kernel with a resident 64-query tile (32 queries = 64 KB per CTA, 10 stages).  Same-box
-    // A/B against the single-CTA resident kernels at 21M rows (gpurun_out/r3j_ab.log, r3k_ab.log): 5.85 vs 6.2 ms at
+    // A/B against the single-CTA resident kernels at 21M rows (profiles/r02_ab/r3j_ab.log, r3k_ab.log): 5.85 vs 6.2 ms at
     // 1-32 queries (7.3 TB/s whole-step), 6.1 vs 6.4 ms at 48, 6.2-6.6 vs 6.6-6.7 ms at 64.  KIRAG_PAIR64=0: single CTA.
     if (nq <= 64 && pair_ok && env_flag("KIRAG_PAIR64", 1) && pair_stages<64, true>(d) >= 6) { plan->bq = 64; plan->resident = 1; plan->pair = 1; }
     else if (nq <= 32 && pick_stages(32, true, d) >= 4) { plan->bq = 32; plan->resident = 1; }
@@ -1125,7 +1125,7 @@ int launch_scan_tc(const void* shadow, int64_t n_rows, int d, const void* qshado
     args.dump_ld = 0;
     // corpus blocks that are re-read once per query tile: evict_last, and evict_first on their LAST read so that dead
     // tiles make room instead of live ones.  DRAM reads of a 21M-row step at batch 4096 (43.0 GB algorithmic; single-pass
-    // ncu, gpurun_out/r2w, r2x): evict_normal 78.6 GB, evict_last 61.8 GB, with the demotion 54.3 GB; time unchanged
+    // ncu, profiles/r02_ab/r2w, r2x): evict_normal 78.6 GB, evict_last 61.8 GB, with the demotion 54.3 GB; time unchanged
     // (DRAM is at 6 %).
     args.x_policy = env_flag("KIRAG_X_POLICY", 3);
     args.pf_tiles = env_flag("KIRAG_PF_TILES", 0);
