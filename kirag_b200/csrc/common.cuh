@@ -201,7 +201,7 @@ int launch_convert_rows(const float* src, int64_t n_rows, int d, int64_t dst_row
 // sums[0..d) += column sums of rows [0, n_rows), sums[d] += sum of squared elements
 int launch_column_sums(const float* src, int64_t n_rows, int d, float* sums, cudaStream_t st);
 // scan_exact.cu
-constexpr int kExactNQ = 4;
+constexpr int kExactNQ = 8;
 int launch_scan_exact(const float* master, int64_t n, int d, const float* q, int nq_valid,
                       float* scores, int64_t ld, int num_sms, cudaStream_t st);
 // rescore.cu

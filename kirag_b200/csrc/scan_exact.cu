@@ -8,7 +8,7 @@
 // fails the exactness certificate.  Scores use the canonical summation order
 // (common.cuh) so they are bit-identical to the rescoring kernel's.
 //
-// HBM-bound: each 4*d-byte row is read once for a group of kExactNQ queries.
+// HBM-bound: each 4*d-byte row is read once for a group of kExactNQ (8) queries.
 // Algorithmic bytes per launch = n*d*4 (+ kExactNQ*n*4 of scores written).
 #include "common.cuh"
 
@@ -34,21 +34,58 @@ scan_exact_kernel(const float* __restrict__ master, int64_t n, int d,
 #pragma unroll
         for (int qi = 0; qi < kExactNQ; ++qi) keep[qi] = 0.0f;
         const int rows = (int)((n - base < 32) ? (n - base) : 32);
-        for (int r = 0; r < rows; ++r) {
-            const float* x = master + (base + r) * (int64_t)d;
-            float acc[kExactNQ];
+        // two rows per trip: every query float4 read from shared memory feeds both rows.  With one row per trip and 8
+        // queries the kernel was bound by shared-memory bandwidth (64 LDS.128 per row and lane: 256 cycles per row
+        // against the 175 cycles per row that the HBM rate allows per SM)
+        for (int r = 0; r < rows; r += 2) {
+            const int rb = (r + 1 < rows) ? r + 1 : r;  // odd tail: the second row repeats the first, its result is unused
+            const float* xa = master + (base + r) * (int64_t)d;
+            const float* xb = master + (base + rb) * (int64_t)d;
+            float acc[2][kExactNQ];
 #pragma unroll
-            for (int qi = 0; qi < kExactNQ; ++qi) acc[qi] = 0.0f;
+            for (int qi = 0; qi < kExactNQ; ++qi) acc[0][qi] = acc[1][qi] = 0.0f;
             if (VEC4) {
-                for (int c = lane * 4; c < d; c += 128) {
-                    const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + c));
+                // the loads of both rows are issued in batches of 4 + 4 before the FMAs that consume them; the FMA
+                // chain of every (row, query) pair — and with it the canonical summation order — is unchanged
+                constexpr int U = 4;
+                int c = lane * 4;
+                for (; c + (U - 1) * 128 < d; c += U * 128) {
+                    float4 va[U], vb[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        va[u] = __ldcs(reinterpret_cast<const float4*>(xa + c + u * 128));
+                        vb[u] = __ldcs(reinterpret_cast<const float4*>(xb + c + u * 128));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+#pragma unroll
+                        for (int qi = 0; qi < kExactNQ; ++qi) {
+                            const float4 qv = *reinterpret_cast<const float4*>(sq + qi * d + c + u * 128);
+                            acc[0][qi] = __fmaf_rn(va[u].x, qv.x, acc[0][qi]);
+                            acc[0][qi] = __fmaf_rn(va[u].y, qv.y, acc[0][qi]);
+                            acc[0][qi] = __fmaf_rn(va[u].z, qv.z, acc[0][qi]);
+                            acc[0][qi] = __fmaf_rn(va[u].w, qv.w, acc[0][qi]);
+                            acc[1][qi] = __fmaf_rn(vb[u].x, qv.x, acc[1][qi]);
+                            acc[1][qi] = __fmaf_rn(vb[u].y, qv.y, acc[1][qi]);
+                            acc[1][qi] = __fmaf_rn(vb[u].z, qv.z, acc[1][qi]);
+                            acc[1][qi] = __fmaf_rn(vb[u].w, qv.w, acc[1][qi]);
+                        }
+                    }
+                }
+                for (; c < d; c += 128) {
+                    const float4 va = __ldcs(reinterpret_cast<const float4*>(xa + c));
+                    const float4 vb = __ldcs(reinterpret_cast<const float4*>(xb + c));
 #pragma unroll
                     for (int qi = 0; qi < kExactNQ; ++qi) {
                         const float4 qv = *reinterpret_cast<const float4*>(sq + qi * d + c);
-                        acc[qi] = __fmaf_rn(xv.x, qv.x, acc[qi]);
-                        acc[qi] = __fmaf_rn(xv.y, qv.y, acc[qi]);
-                        acc[qi] = __fmaf_rn(xv.z, qv.z, acc[qi]);
-                        acc[qi] = __fmaf_rn(xv.w, qv.w, acc[qi]);
+                        acc[0][qi] = __fmaf_rn(va.x, qv.x, acc[0][qi]);
+                        acc[0][qi] = __fmaf_rn(va.y, qv.y, acc[0][qi]);
+                        acc[0][qi] = __fmaf_rn(va.z, qv.z, acc[0][qi]);
+                        acc[0][qi] = __fmaf_rn(va.w, qv.w, acc[0][qi]);
+                        acc[1][qi] = __fmaf_rn(vb.x, qv.x, acc[1][qi]);
+                        acc[1][qi] = __fmaf_rn(vb.y, qv.y, acc[1][qi]);
+                        acc[1][qi] = __fmaf_rn(vb.z, qv.z, acc[1][qi]);
+                        acc[1][qi] = __fmaf_rn(vb.w, qv.w, acc[1][qi]);
                     }
                 }
             } else {
@@ -56,18 +93,23 @@ scan_exact_kernel(const float* __restrict__ master, int64_t n, int d,
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (c + j < d) {
-                            const float xv = x[c + j];
+                            const float va = xa[c + j], vb = xb[c + j];
 #pragma unroll
-                            for (int qi = 0; qi < kExactNQ; ++qi)
-                                acc[qi] = __fmaf_rn(xv, sq[qi * d + c + j], acc[qi]);
+                            for (int qi = 0; qi < kExactNQ; ++qi) {
+                                const float qv = sq[qi * d + c + j];
+                                acc[0][qi] = __fmaf_rn(va, qv, acc[0][qi]);
+                                acc[1][qi] = __fmaf_rn(vb, qv, acc[1][qi]);
+                            }
                         }
                     }
                 }
             }
 #pragma unroll
             for (int qi = 0; qi < kExactNQ; ++qi) {
-                const float t = warp_butterfly_sum(acc[qi]);
-                if (lane == r) keep[qi] = t;
+                const float ta = warp_butterfly_sum(acc[0][qi]);
+                const float tb = warp_butterfly_sum(acc[1][qi]);
+                if (lane == r) keep[qi] = ta;
+                if (rb != r && lane == rb) keep[qi] = tb;
             }
         }
         if (lane < rows) {
