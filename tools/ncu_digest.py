@@ -23,6 +23,9 @@ def launches(path: str, first: str):
     """Launch list of `bench.py`: take the LAST complete search (from a launch matching `first` up to, but
     excluding, the next one) and print every kernel's device time and share."""
     rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 14 and r[0].isdigit()]
+    # a list captured with several metrics has one line per (launch, metric): keep the duration lines
+    if any(r[12] != "gpu__time_duration.sum" for r in rows):
+        rows = [r for r in rows if r[12] == "gpu__time_duration.sum"]
     names = [r[4] for r in rows]
     starts = [i for i, n in enumerate(names) if re.search(first, n)]
     assert len(starts) >= 2, "need at least two searches in the launch list"
